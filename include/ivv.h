@@ -1,0 +1,134 @@
+/*
+ * ivv.h — C ABI of libivv_b200.so: the sm_100a kernels behind the InsV2V denoising hot path.
+ *
+ * The reference (amazon-science/instruct-video-to-video) is pure Python/PyTorch and has no FFI of its own; each entry
+ * point below replaces the library call that the cited reference line dispatches to.
+ * Contract: the caller (PyTorch) owns every buffer; the library never allocates device memory, keeps no
+ * pointer after return, enqueues on the caller's stream, never synchronises, and is CUDA-graph capturable.
+ * Return value: 0 = ok, non-zero = error; the message is available from ivv_last_error() (thread-local).
+ *
+ * Layout vocabulary: activations are channels-last fp16 "frames": [n_img, h, w, c] with n_img = clips*frames
+ * (so the reference's `(b f)` fold, resnet.py:14, is a free view); "tokens" [rows, c] is the same memory.
+ */
+#ifndef IVV_H_
+#define IVV_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ivv_stream_t; /* cudaStream_t */
+
+#define IVV_ABI_VERSION 1
+
+int ivv_abi_version(void);
+const char* ivv_last_error(void);
+
+/* ---- K1/K2/K11: tcgen05 implicit-GEMM convolution / linear --------------------------------------------------
+ * Replaces InflatedConv3d.forward (modules/video_unet_temporal/resnet.py:10-18), nn.Linear inside diffusers
+ * Attention/FeedForward (called at attention.py:241-259, motion_module.py:104,126,289-301,327), nn.Conv2d in the
+ * VAE decoder (modules/vqvae/model.py:86-136,386-408).
+ *   D[pix, co] = sum_{tap, ci} A[pix + tap_offset, ci] * Wt[tap][co][ci]  (+bias[co]) (+rowbias[pix/group][co])
+ *                (+residual[pix, co]);  GEGLU: D[pix, j] = (acc_h + b_h) * gelu_erf(acc_g + b_g)
+ * taps = 1 (Linear / 1x1 conv; h = n_img = 1, w = rows is allowed) or 9 (3x3, stride 1, zero pad 1).               */
+typedef struct {
+  const void* a;      /* fp16 [n_img, h, w, a_ld] (first c channels used)                                     */
+  int64_t n_img, h, w, c, a_ld;
+  const void* wgt;    /* fp16 [taps][n_out][w_ld]  (w_ld >= c, multiple of 8, zero padded)                     */
+  int64_t n_out, w_ld;
+  int32_t taps;       /* 1 or 9                                                                                */
+  int32_t geglu;      /* 1: weight rows are tile-interleaved [64 hidden | 64 gate]; output width n_out/2        */
+  void* d;            /* fp16 (or fp32 when out_f32) [n_img*h*w, d_ld]                                         */
+  int64_t d_ld;
+  int32_t out_f32;
+  int32_t reserved;
+  const void* bias;     /* fp16 [n_out] or NULL (GEGLU: same tile-interleaved order as wgt rows)               */
+  const void* rowbias;  /* fp16 [groups, rowbias_ld] or NULL: added to every pixel of group pix/rowbias_group  */
+  int64_t rowbias_group, rowbias_ld;
+  const void* residual; /* fp16 [n_img*h*w, res_ld] or NULL                                                    */
+  int64_t res_ld;
+} ivv_gemm_args;
+int ivv_gemm(const ivv_gemm_args* args, ivv_stream_t stream);
+
+/* im2col for the stride-2 3x3 convolutions (Downsample3D, resnet.py:99-107): out[n,ho,wo, tap*c + ci], pad 1.   */
+int ivv_im2col_s2(const void* x, void* out, int64_t n_img, int64_t h, int64_t w, int64_t c, int64_t ho, int64_t wo,
+                  ivv_stream_t stream);
+
+/* ---- K6/K7: GroupNorm (+SiLU) ------------------------------------------------------------------------------
+ * Replaces torch.nn.GroupNorm + F.silu at resnet.py:177-178,188-194, unet.py:427-428 (5-D: statistics span
+ * frames_per_group = F frames) and attention.py:101, motion_module.py:136, vqvae/model.py:31-32 (per frame: 1).
+ * x,y: fp16 [n_img, hw, c]; stats workspace: double [n_img/frames_per_group, groups, 2], zeroed by the call.    */
+int ivv_groupnorm(const void* x, void* y, const void* gamma, const void* beta, int64_t n_img, int64_t hw, int64_t c,
+                  int32_t groups, int64_t frames_per_group, float eps, int32_t silu, void* stats_ws,
+                  size_t stats_ws_bytes, ivv_stream_t stream);
+size_t ivv_groupnorm_ws_bytes(int64_t n_img, int32_t groups, int64_t frames_per_group);
+
+/* ---- K8: LayerNorm (+ temporal positional encoding) ---------------------------------------------------------
+ * Replaces nn.LayerNorm at attention.py:168,185,191 / motion_module.py:195,201 and, when pe != NULL, the
+ * PositionalEncoding add of motion_module.py:236-242 (pe fp32 [pe_len, c], frame = (row / rows_per_frame) % frames,
+ * pe row = pe_start + frame).                                                                                  */
+int ivv_layernorm(const void* x, void* y, const void* gamma, const void* beta, int64_t rows, int64_t c, float eps,
+                  const float* pe, int64_t rows_per_frame, int64_t frames, int64_t pe_start, ivv_stream_t stream);
+
+/* ---- K3/K4: fused flash attention (tcgen05 + TMEM + TMA) ----------------------------------------------------
+ * Replaces diffusers Attention core / xformers.memory_efficient_attention called at attention.py:241-256.
+ * q: fp16 rows [n_batch*s_q, q_ld], head hd at columns [hd*d, hd*d+d); k, v likewise with kv batch = batch/kv_div
+ * (kv_div = frames for cross-attention: the per-clip context is shared by all frames, attention.py:96).
+ * o: fp16 [n_batch*s_q, o_ld].  softmax(q k^T * scale) v, fp32 statistics.                                     */
+int ivv_attention(const void* q, int64_t q_ld, const void* k, const void* v, int64_t kv_ld, void* o, int64_t o_ld,
+                  int64_t n_batch, int64_t s_q, int64_t s_kv, int64_t kv_div, int32_t heads, int32_t d, float scale,
+                  ivv_stream_t stream);
+
+/* ---- K5: temporal self-attention over frames (HBM-bound, L = frames <= 32) ----------------------------------
+ * Replaces VersatileAttention.forward core, motion_module.py:275,303-334, without either transpose copy:
+ * qkv fp16 [clips*frames*hw, 3c] (q | k | v); sequences run over the frame index at fixed (clip, pixel).        */
+int ivv_temporal_attention(const void* qkv, void* o, int64_t clips, int64_t frames, int64_t hw, int64_t c,
+                           int32_t heads, float scale, ivv_stream_t stream);
+
+/* ---- row softmax for the materialised VAE attention (vqvae/model.py:183-186) ------------------------------- */
+int ivv_softmax_rows(const void* x, void* y, int64_t rows, int64_t cols, float scale, ivv_stream_t stream);
+
+/* ---- K9 and layout glue -------------------------------------------------------------------------------------*/
+/* nearest 2x upsample of frames (resnet.py:59-61, vqvae/model.py:48): [n,h,w,c] -> [n,2h,2w,c] (or to ho,wo)     */
+int ivv_upsample_nearest(const void* x, void* y, int64_t n_img, int64_t h, int64_t w, int64_t c, int64_t ho,
+                         int64_t wo, ivv_stream_t stream);
+/* channel concat (unet_blocks.py:561,659): y[rows, ca+cb] = [a | b]                                            */
+int ivv_concat_channels(const void* a, int64_t ca, const void* b, int64_t cb, void* y, int64_t rows,
+                        ivv_stream_t stream);
+/* [b, c, f, h, w] (fp32 or fp16) -> frames [b*f, h, w, c_pad] fp16 (channels >= c zero)                          */
+int ivv_ncfhw_to_frames(const void* x, int32_t x_is_f32, void* y, int64_t b, int64_t c, int64_t f, int64_t hw,
+                        int64_t c_pad, ivv_stream_t stream);
+/* frames [b*f, hw, ld] (fp16 or fp32, first c channels) -> [b, c, f, h, w] fp32 or fp16                          */
+int ivv_frames_to_ncfhw(const void* x, int32_t x_is_f32, int64_t ld, void* y, int32_t y_is_f32, int64_t b,
+                        int64_t c, int64_t f, int64_t hw, ivv_stream_t stream);
+/* sinusoidal timestep projection (diffusers Timesteps, called at unet.py:358): t[n] -> fp16 [n, dim] (cos | sin)  */
+int ivv_timestep_embedding(const float* t, void* y, int64_t n, int32_t dim, int32_t flip_sin_to_cos,
+                           float freq_shift, ivv_stream_t stream);
+/* y = silu(x) elementwise, fp16                                                                                */
+int ivv_silu(const void* x, void* y, int64_t n, ivv_stream_t stream);
+/* y = a * x + b (fp16 in, fp16 out) — latent scaling (diffusion.py:247-249)                                      */
+int ivv_scale(const void* x, void* y, int64_t n, float a, float b, ivv_stream_t stream);
+
+/* ---- K12: optical-flow motion compensation -------------------------------------------------------------------
+ * ivv_warp_image: misc_utils/flow_utils.py:25-57 (bilinear, zeros padding, align_corners=True), NCHW fp32.
+ * ivv_resize_flow: flow_utils.py:59-86 (scale u,v then bilinear align_corners=False), NCHW fp32.
+ * ivv_flow_noise_correction: the whole per-step loop pl_trainer/inference/inference.py:374-386 in one launch:
+ *   for each query frame q: eps[q] += where(sum_r mask > 0.5, sum_r warp(delta[r], flow[q,r]) / sum_r mask, 0).   */
+int ivv_warp_image(const float* image, const float* flow, float* out, int64_t n, int64_t c, int64_t h, int64_t w,
+                   ivv_stream_t stream);
+int ivv_resize_flow(const float* flow, float* out, int64_t n, int64_t h, int64_t w, int64_t ho, int64_t wo,
+                    ivv_stream_t stream);
+int ivv_flow_noise_correction(const float* delta_ref, const float* flow_lat, float* eps, int64_t q, int64_t r,
+                              int64_t c, int64_t h, int64_t w, ivv_stream_t stream);
+
+/* ---- K13: classifier-free-guidance combine + DDIM update (inference.py:198-210) ------------------------------
+ * eps3: fp32 [3, n] (branches uncond | image | text+image); latent fp32 [n] updated in place.                   */
+int ivv_cfg_ddim_step(const float* eps3, float* latent, float* eps_out, int64_t n, float text_cfg, float img_cfg,
+                      float alpha_prod_t, float alpha_prod_prev, ivv_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IVV_H_ */

@@ -1,0 +1,264 @@
+// Data-movement and elementwise glue kernels (HBM-bound, 16-byte vectors where the layout allows).
+// Reference call sites: ivv.h (K9, K13 and layout glue).
+#include "../../include/ivv.h"
+#include "common.cuh"
+
+namespace ivv {
+
+// out[n, ho, wo, tap*c + ci] = x[n, 2*ho + ky - 1, 2*wo + kx - 1, ci]  (zero outside), tap = ky*3+kx
+__global__ void im2col_s2_kernel(const __half* __restrict__ x, __half* __restrict__ out, long long n_img, int h, int w,
+                                 int c, int ho, int wo) {
+  const int V = c / 8;
+  const long long total = n_img * ho * wo * 9 * V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int vec = (int)(i % V);
+    long long t = i / V;
+    const int tap = (int)(t % 9);
+    t /= 9;
+    const int ox = (int)(t % wo);
+    t /= wo;
+    const int oy = (int)(t % ho);
+    const long long n = t / ho;
+    const int iy = 2 * oy + tap / 3 - 1;
+    const int ix = 2 * ox + tap % 3 - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < h && ix >= 0 && ix < w)
+      v = *reinterpret_cast<const uint4*>(x + ((n * h + iy) * w + ix) * c + vec * 8);
+    *reinterpret_cast<uint4*>(out + i * 8) = v;
+  }
+}
+
+__global__ void upsample_nearest_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long n_img, int h,
+                                        int w, int c, int ho, int wo) {
+  const int V = c / 8;
+  const long long total = n_img * ho * wo * V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int vec = (int)(i % V);
+    long long t = i / V;
+    const int ox = (int)(t % wo);
+    t /= wo;
+    const int oy = (int)(t % ho);
+    const long long n = t / ho;
+    // PyTorch 'nearest': src = floor(dst * in / out)
+    const int iy = min((int)(((long long)oy * h) / ho), h - 1);
+    const int ix = min((int)(((long long)ox * w) / wo), w - 1);
+    *reinterpret_cast<uint4*>(y + i * 8) = *reinterpret_cast<const uint4*>(x + ((n * h + iy) * w + ix) * c + vec * 8);
+  }
+}
+
+__global__ void concat_channels_kernel(const __half* __restrict__ a, int ca, const __half* __restrict__ b, int cb,
+                                       __half* __restrict__ y, long long rows) {
+  const int Va = ca / 8, Vb = cb / 8, V = Va + Vb;
+  const long long total = rows * V;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int vec = (int)(i % V);
+    const long long r = i / V;
+    uint4 v;
+    if (vec < Va)
+      v = *reinterpret_cast<const uint4*>(a + r * ca + vec * 8);
+    else
+      v = *reinterpret_cast<const uint4*>(b + r * cb + (vec - Va) * 8);
+    *reinterpret_cast<uint4*>(y + i * 8) = v;
+  }
+}
+
+template <typename TIn>
+__global__ void ncfhw_to_frames_kernel(const TIn* __restrict__ x, __half* __restrict__ y, long long b, int c, int f,
+                                       long long hw, int c_pad) {
+  const long long total = b * f * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % hw;
+    const long long bf = i / hw;
+    const int fi = (int)(bf % f);
+    const long long bi = bf / f;
+    __half* yo = y + i * c_pad;
+    for (int ch = 0; ch < c_pad; ++ch) {
+      float v = 0.f;
+      if (ch < c) v = (float)x[((bi * c + ch) * f + fi) * hw + pix];
+      yo[ch] = __float2half_rn(v);
+    }
+  }
+}
+
+template <typename TIn, typename TOut>
+__global__ void frames_to_ncfhw_kernel(const TIn* __restrict__ x, long long ld, TOut* __restrict__ y, long long b,
+                                       int c, int f, long long hw) {
+  const long long total = b * f * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i % hw;
+    const long long bf = i / hw;
+    const int fi = (int)(bf % f);
+    const long long bi = bf / f;
+    const TIn* xi = x + i * ld;
+    for (int ch = 0; ch < c; ++ch) y[((bi * c + ch) * f + fi) * hw + pix] = (TOut)(float)xi[ch];
+  }
+}
+
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, __half* __restrict__ y, int n, int dim,
+                                          int flip, float freq_shift) {
+  const int half_dim = dim / 2;
+  const int total = n * half_dim;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i % half_dim;
+    const int r = i / half_dim;
+    const float freq = expf(-logf(10000.f) * (float)k / ((float)half_dim - freq_shift));
+    const float arg = t[r] * freq;
+    const float s = sinf(arg), co = cosf(arg);
+    __half* yr = y + (long long)r * dim;
+    if (flip) {
+      yr[k] = __float2half_rn(co);
+      yr[half_dim + k] = __float2half_rn(s);
+    } else {
+      yr[k] = __float2half_rn(s);
+      yr[half_dim + k] = __float2half_rn(co);
+    }
+  }
+}
+
+__global__ void silu_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2half_rn(silu_f(__half2float(x[i])));
+}
+
+__global__ void scale_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long n, float a, float b) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = __float2half_rn(__half2float(x[i]) * a + b);
+}
+
+// eps = e1 + img_cfg (e2 - e1) + text_cfg (e3 - e2);  DDIM (eta = 0, epsilon prediction, no clipping)
+__global__ void cfg_ddim_kernel(const float* __restrict__ eps3, float* __restrict__ latent, float* __restrict__ eps_out,
+                                long long n, float text_cfg, float img_cfg, float sqrt_at, float sqrt_1mat,
+                                float sqrt_ap, float sqrt_1map) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float e1 = eps3[i], e2 = eps3[n + i], e3 = eps3[2 * n + i];
+    const float e = e1 + img_cfg * (e2 - e1) + text_cfg * (e3 - e2);
+    const float x = latent[i];
+    const float x0 = (x - sqrt_1mat * e) / sqrt_at;
+    latent[i] = sqrt_ap * x0 + sqrt_1map * e;
+    if (eps_out) eps_out[i] = e;
+  }
+}
+
+static inline unsigned grid_for(long long total, int threads) {
+  long long b = (total + threads - 1) / threads;
+  const long long cap = 148LL * 16;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace ivv
+
+using namespace ivv;
+#define STREAM reinterpret_cast<cudaStream_t>(stream_)
+
+extern "C" int ivv_im2col_s2(const void* x, void* out, int64_t n_img, int64_t h, int64_t w, int64_t c, int64_t ho,
+                             int64_t wo, ivv_stream_t stream_) {
+  IVV_REQUIRE(x && out && n_img > 0 && c % 8 == 0, "ivv_im2col_s2: bad arguments (c must be a multiple of 8)");
+  IVV_REQUIRE(ho == (h - 1) / 2 + 1 && wo == (w - 1) / 2 + 1, "ivv_im2col_s2: output size must be (h-1)/2+1");
+  const long long total = n_img * ho * wo * 9 * (c / 8);
+  im2col_s2_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(reinterpret_cast<const __half*>(x),
+                                                             reinterpret_cast<__half*>(out), n_img, (int)h, (int)w,
+                                                             (int)c, (int)ho, (int)wo);
+  IVV_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ivv_upsample_nearest(const void* x, void* y, int64_t n_img, int64_t h, int64_t w, int64_t c, int64_t ho,
+                                    int64_t wo, ivv_stream_t stream_) {
+  IVV_REQUIRE(x && y && n_img > 0 && c % 8 == 0, "ivv_upsample_nearest: bad arguments (c must be a multiple of 8)");
+  const long long total = n_img * ho * wo * (c / 8);
+  upsample_nearest_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(reinterpret_cast<const __half*>(x),
+                                                                    reinterpret_cast<__half*>(y), n_img, (int)h, (int)w,
+                                                                    (int)c, (int)ho, (int)wo);
+  IVV_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ivv_concat_channels(const void* a, int64_t ca, const void* b, int64_t cb, void* y, int64_t rows,
+                                   ivv_stream_t stream_) {
+  IVV_REQUIRE(a && b && y && rows > 0 && ca % 8 == 0 && cb % 8 == 0, "ivv_concat_channels: bad arguments");
+  const long long total = rows * ((ca + cb) / 8);
+  concat_channels_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(reinterpret_cast<const __half*>(a), (int)ca,
+                                                                   reinterpret_cast<const __half*>(b), (int)cb,
+                                                                   reinterpret_cast<__half*>(y), rows);
+  IVV_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ivv_ncfhw_to_frames(const void* x, int32_t x_is_f32, void* y, int64_t b, int64_t c, int64_t f,
+                                   int64_t hw, int64_t c_pad, ivv_stream_t stream_) {
+  IVV_REQUIRE(x && y && b > 0 && c > 0 && f > 0 && hw > 0 && c_pad >= c, "ivv_ncfhw_to_frames: bad arguments");
+  const long long total = b * f * hw;
+  if (x_is_f32)
+    ncfhw_to_frames_kernel<float><<<grid_for(total, 256), 256, 0, STREAM>>>(
+        reinterpret_cast<const float*>(x), reinterpret_cast<__half*>(y), b, (int)c, (int)f, hw, (int)c_pad);
+  else
+    ncfhw_to_frames_kernel<__half><<<grid_for(total, 256), 256, 0, STREAM>>>(
+        reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), b, (int)c, (int)f, hw, (int)c_pad);
+  IVV_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ivv_frames_to_ncfhw(const void* x, int32_t x_is_f32, int64_t ld, void* y, int32_t y_is_f32, int64_t b,
+                                   int64_t c, int64_t f, int64_t hw, ivv_stream_t stream_) {
+  IVV_REQUIRE(x && y && b > 0 && c > 0 && f > 0 && hw > 0 && ld >= c, "ivv_frames_to_ncfhw: bad arguments");
+  const long long total = b * f * hw;
+  const unsigned g = grid_for(total, 256);
+  if (x_is_f32 && y_is_f32)
+    frames_to_ncfhw_kernel<float, float><<<g, 256, 0, STREAM>>>(reinterpret_cast<const float*>(x), ld,
+                                                                reinterpret_cast<float*>(y), b, (int)c, (int)f, hw);
+  else if (x_is_f32)
+    frames_to_ncfhw_kernel<float, __half><<<g, 256, 0, STREAM>>>(reinterpret_cast<const float*>(x), ld,
+                                                                 reinterpret_cast<__half*>(y), b, (int)c, (int)f, hw);
+  else if (y_is_f32)
+    frames_to_ncfhw_kernel<__half, float><<<g, 256, 0, STREAM>>>(reinterpret_cast<const __half*>(x), ld,
+                                                                 reinterpret_cast<float*>(y), b, (int)c, (int)f, hw);
+  else
+    frames_to_ncfhw_kernel<__half, __half><<<g, 256, 0, STREAM>>>(reinterpret_cast<const __half*>(x), ld,
+                                                                  reinterpret_cast<__half*>(y), b, (int)c, (int)f, hw);
+  IVV_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ivv_timestep_embedding(const float* t, void* y, int64_t n, int32_t dim, int32_t flip_sin_to_cos,
+                                      float freq_shift, ivv_stream_t stream_) {
+  IVV_REQUIRE(t && y && n > 0 && dim > 0 && dim % 2 == 0, "ivv_timestep_embedding: bad arguments");
+  timestep_embedding_kernel<<<grid_for(n * dim / 2, 128), 128, 0, STREAM>>>(t, reinterpret_cast<__half*>(y), (int)n,
+                                                                            dim, flip_sin_to_cos, freq_shift);
+  IVV_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ivv_silu(const void* x, void* y, int64_t n, ivv_stream_t stream_) {
+  IVV_REQUIRE(x && y && n > 0, "ivv_silu: bad arguments");
+  silu_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y),
+                                                    n);
+  IVV_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ivv_scale(const void* x, void* y, int64_t n, float a, float b, ivv_stream_t stream_) {
+  IVV_REQUIRE(x && y && n > 0, "ivv_scale: bad arguments");
+  scale_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y),
+                                                     n, a, b);
+  IVV_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ivv_cfg_ddim_step(const float* eps3, float* latent, float* eps_out, int64_t n, float text_cfg,
+                                 float img_cfg, float alpha_prod_t, float alpha_prod_prev, ivv_stream_t stream_) {
+  IVV_REQUIRE(eps3 && latent && n > 0, "ivv_cfg_ddim_step: bad arguments");
+  IVV_REQUIRE(alpha_prod_t > 0.f && alpha_prod_t <= 1.f && alpha_prod_prev > 0.f && alpha_prod_prev <= 1.f,
+              "ivv_cfg_ddim_step: alphas must be in (0, 1]");
+  cfg_ddim_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(eps3, latent, eps_out, n, text_cfg, img_cfg,
+                                                        sqrtf(alpha_prod_t), sqrtf(1.f - alpha_prod_t),
+                                                        sqrtf(alpha_prod_prev), sqrtf(1.f - alpha_prod_prev));
+  IVV_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

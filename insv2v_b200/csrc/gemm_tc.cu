@@ -1,0 +1,421 @@
+// tcgen05 implicit-GEMM convolution / linear for sm_100a.
+//
+//   D[pix, co] = sum_{tap, ci} A[pix (+tap shift), ci] * W[tap][co][ci]     fp16 x fp16 -> fp32 (TMEM) -> fp16/fp32
+//
+// A is a channels-last activation tensor [n_img, h, w, c]. One CTA computes a 128-pixel x BLOCK_N tile. The 128 pixels
+// are a (bw x bh x bn) box of the (w, h, n_img) index space, fetched per filter tap as ONE 4-D TMA box whose start
+// coordinate is shifted by the tap offset: the zero padding of the 3x3 convolution is TMA out-of-bounds zero fill, and
+// no im2col buffer ever exists. A Linear layer is the same kernel with taps = 1 and box (128, 1, 1).
+// Warp roles: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+TMEM owner), warps 2..5 = epilogue
+// (tcgen05.ld -> bias / temb row-bias / residual / GEGLU -> global).  Reference call sites: ivv.h (K1/K2/K11).
+#include "../../include/ivv.h"
+#include "common.cuh"
+
+namespace ivv {
+
+struct GemmKParams {
+  int bw, bh, bn;                 // A box (pixels); bw*bh*bn == 128
+  int tiles_w, tiles_h, tiles_g;  // tiles along w, h and image groups
+  int W, H, NI;                   // output extent
+  int kblocks;                    // ceil(c / 64) per tap
+  int taps;                       // 1 or 9
+  int n_out;                      // GEMM N (weight rows)
+  int out_cols;                   // columns written (n_out, or n_out/2 for GEGLU)
+  int geglu, out_f32;
+  void* d;
+  long long d_ld;
+  const __half* bias;
+  const __half* rowbias;
+  long long rowbias_group, rowbias_ld;
+  const __half* residual;
+  long long res_ld;
+};
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
+constexpr int kGemmThreads = 192;
+
+template <int BN>
+constexpr uint32_t tmem_cols_for() {
+  return BN <= 32 ? 32u : BN <= 64 ? 64u : BN <= 128 ? 128u : 256u;
+}
+
+template <int BN, int STAGES>
+constexpr int gemm_smem_bytes() {
+  return STAGES * (kABytes + BN * 128) + 256 /*barriers + tmem ptr*/;
+}
+
+__device__ __forceinline__ void store8(void* d, bool f32, long long off, const float (&v)[8], int nvalid, bool vec_ok) {
+  if (f32) {
+    float* p = reinterpret_cast<float*>(d) + off;
+    if (nvalid == 8 && vec_ok) {
+      reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+      reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      for (int j = 0; j < nvalid; ++j) p[j] = v[j];
+    }
+  } else {
+    __half* p = reinterpret_cast<__half*>(d) + off;
+    if (nvalid == 8 && vec_ok) {
+      __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+      __half2 h2 = __floats2half2_rn(v[4], v[5]), h3 = __floats2half2_rn(v[6], v[7]);
+      uint4 u;
+      u.x = *reinterpret_cast<uint32_t*>(&h0);
+      u.y = *reinterpret_cast<uint32_t*>(&h1);
+      u.z = *reinterpret_cast<uint32_t*>(&h2);
+      u.w = *reinterpret_cast<uint32_t*>(&h3);
+      *reinterpret_cast<uint4*>(p) = u;
+    } else {
+      for (int j = 0; j < nvalid; ++j) p[j] = __float2half_rn(v[j]);
+    }
+  }
+}
+
+__device__ __forceinline__ void load8h(const __half* p, int nvalid, bool vec_ok, float (&v)[8]) {
+  if (nvalid == 8 && vec_ok) {
+    uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 f = __half22float2(h[j]);
+      v[2 * j] = f.x;
+      v[2 * j + 1] = f.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = j < nvalid ? __half2float(p[j]) : 0.f;
+  }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ GemmKParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-byte alignment
+  constexpr int kStageBytes = kABytes + BN * 128;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int ntile = blockIdx.x;
+  const int mtile = blockIdx.y;
+  // tile -> pixel box origin
+  const int tw = mtile % p.tiles_w;
+  const int th = (mtile / p.tiles_w) % p.tiles_h;
+  const int tg = mtile / (p.tiles_w * p.tiles_h);
+  const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tg * p.bn;
+  const int total_it = p.taps * p.kblocks;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<tmem_cols_for<BN>()>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < total_it; ++it) {
+        const int tap = it / p.kblocks;
+        const int kb = it - tap * p.kblocks;
+        int dy = 0, dx = 0;
+        if (p.taps == 9) {
+          dy = tap / 3 - 1;
+          dx = tap % 3 - 1;
+        }
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * kStageBytes;
+        uint8_t* sb = sa + kABytes;
+        mbar_expect_tx(&full_bar[stage], kStageBytes);
+        tma_load_4d(sa, &tmA, &full_bar[stage], kb * kBlockK, w0 + dx, h0 + dy, n0);
+        tma_load_3d(sb, &tmB, &full_bar[stage], kb * kBlockK, ntile * BN, tap);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = umma_idesc_f16(kBlockM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < total_it; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+        const uint64_t adesc = umma_desc_kmajor_sw128(sa);
+        const uint64_t bdesc = umma_desc_kmajor_sw128(sa + kABytes);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          // advance 16 fp16 = 32 B along K inside the 128-B swizzle atom: +2 in the (addr >> 4) field
+          umma_f16_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue: 4 warps, warp w owns TMEM lanes 32*(w%4) .. +32 =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int wi = r % p.bw;
+    const int hi = (r / p.bw) % p.bh;
+    const int ni = r / (p.bw * p.bh);
+    const int w = w0 + wi, h = h0 + hi, n = n0 + ni;
+    const bool valid = (w < p.W) && (h < p.H) && (n < p.NI);
+    const long long pix = (static_cast<long long>(n) * p.H + h) * p.W + w;
+    const bool d_vec = (p.d_ld % 8) == 0 && ((reinterpret_cast<uintptr_t>(p.d) & 31) == 0);
+    const bool r_vec = p.residual && (p.res_ld % 8) == 0 && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+    const __half* rb = p.rowbias ? p.rowbias + (pix / p.rowbias_group) * p.rowbias_ld : nullptr;
+
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+
+    if (!p.geglu) {
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t acc[32];
+        tmem_ld32(taddr + c, acc);
+        tmem_ld_wait();
+        const int col0 = ntile * BN + c;
+        if (valid && col0 < p.n_out) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int col = col0 + g * 8;
+            const int nv = min(8, p.n_out - col);
+            if (nv <= 0) break;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (j < nv) v[j] += __half2float(p.bias[col + j]);
+            }
+            if (rb) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (j < nv) v[j] += __half2float(rb[col + j]);
+            }
+            if (p.residual) {
+              float rv[8];
+              load8h(p.residual + pix * p.res_ld + col, nv, r_vec, rv);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += rv[j];
+            }
+            store8(p.d, p.out_f32 != 0, pix * p.d_ld + col, v, nv, d_vec);
+          }
+        }
+      }
+    } else {
+      // GEGLU: tile columns [0, BN/2) = hidden, [BN/2, BN) = gate of the same output columns
+      constexpr int HALF = BN / 2;
+#pragma unroll 1
+      for (int c = 0; c < HALF; c += 32) {
+        uint32_t hacc[32], gacc[32];
+        tmem_ld32(taddr + c, hacc);
+        tmem_ld32(taddr + HALF + c, gacc);
+        tmem_ld_wait();
+        const int bcol0 = ntile * BN + c;      // position of hidden bias in the interleaved bias vector
+        const int ocol0 = ntile * HALF + c;    // output column
+        if (valid && ocol0 < p.out_cols) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int ocol = ocol0 + g * 8;
+            const int nv = min(8, p.out_cols - ocol);
+            if (nv <= 0) break;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float hv = __uint_as_float(hacc[g * 8 + j]);
+              float gv = __uint_as_float(gacc[g * 8 + j]);
+              if (p.bias && j < nv) {
+                hv += __half2float(p.bias[bcol0 + g * 8 + j]);
+                gv += __half2float(p.bias[bcol0 + HALF + g * 8 + j]);
+              }
+              v[j] = hv * gelu_erf_f(gv);
+            }
+            store8(p.d, p.out_f32 != 0, pix * p.d_ld + ocol, v, nv, d_vec);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<tmem_cols_for<BN>()>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+static int pow2_floor_div(long long x, int cap) {
+  int b = 1;
+  while (b * 2 <= cap && (x % (b * 2)) == 0) b *= 2;
+  return b;
+}
+static int pow2_ceil(long long x) {
+  int b = 1;
+  while (b < x) b *= 2;
+  return b;
+}
+
+// choose the (bw, bh, bn) pixel box with bw*bh*bn = 128 that minimises the number of M tiles
+static void choose_box(long long W, long long H, long long NI, int* bw, int* bh, int* bn) {
+  long long best = -1;
+  for (int cw = 1; cw <= 128; cw *= 2) {
+    for (int ch = 1; cw * ch <= 128; ch *= 2) {
+      const int cn = 128 / (cw * ch);
+      const long long tiles = ((W + cw - 1) / cw) * ((H + ch - 1) / ch) * ((NI + cn - 1) / cn);
+      // prefer fewer tiles; tie -> wider rows (longer contiguous runs in memory)
+      if (best < 0 || tiles < best || (tiles == best && cw > *bw)) {
+        best = tiles;
+        *bw = cw;
+        *bh = ch;
+        *bn = cn;
+      }
+    }
+  }
+  (void)pow2_floor_div;
+  (void)pow2_ceil;
+}
+
+template <int BN, int STAGES>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& kp, int m_tiles, int n_tiles,
+                  cudaStream_t stream) {
+  constexpr int smem = gemm_smem_bytes<BN, STAGES>();
+  static bool configured = false;
+  if (!configured) {
+    IVV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid(n_tiles, m_tiles, 1);
+  gemm_tc_kernel<BN, STAGES><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, kp);
+  IVV_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace ivv
+
+extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
+  using namespace ivv;
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  IVV_REQUIRE(a != nullptr, "ivv_gemm: null args");
+  IVV_REQUIRE(a->taps == 1 || a->taps == 9, "ivv_gemm: taps must be 1 or 9, got %d", a->taps);
+  IVV_REQUIRE(a->a && a->wgt && a->d, "ivv_gemm: null tensor pointer");
+  IVV_REQUIRE(a->n_img > 0 && a->h > 0 && a->w > 0 && a->c > 0 && a->n_out > 0, "ivv_gemm: empty problem");
+  IVV_REQUIRE(a->a_ld % 8 == 0 && a->w_ld % 8 == 0, "ivv_gemm: a_ld (%lld) and w_ld (%lld) must be multiples of 8",
+              (long long)a->a_ld, (long long)a->w_ld);
+  IVV_REQUIRE(a->c <= a->a_ld && a->c <= a->w_ld, "ivv_gemm: c exceeds a leading dimension");
+  IVV_REQUIRE(!a->geglu || (a->n_out % 128 == 0), "ivv_gemm: GEGLU needs n_out %% 128 == 0");
+  IVV_REQUIRE(!(a->geglu && (a->rowbias || a->residual)), "ivv_gemm: GEGLU epilogue takes bias only");
+
+  GemmKParams kp{};
+  choose_box(a->w, a->h, a->n_img, &kp.bw, &kp.bh, &kp.bn);
+  kp.tiles_w = (int)((a->w + kp.bw - 1) / kp.bw);
+  kp.tiles_h = (int)((a->h + kp.bh - 1) / kp.bh);
+  kp.tiles_g = (int)((a->n_img + kp.bn - 1) / kp.bn);
+  kp.W = (int)a->w;
+  kp.H = (int)a->h;
+  kp.NI = (int)a->n_img;
+  kp.kblocks = (int)((a->c + kBlockK - 1) / kBlockK);
+  kp.taps = a->taps;
+  kp.n_out = (int)a->n_out;
+  kp.geglu = a->geglu;
+  kp.out_cols = a->geglu ? (int)(a->n_out / 2) : (int)a->n_out;
+  kp.out_f32 = a->out_f32;
+  kp.d = a->d;
+  kp.d_ld = a->d_ld;
+  kp.bias = reinterpret_cast<const __half*>(a->bias);
+  kp.rowbias = reinterpret_cast<const __half*>(a->rowbias);
+  kp.rowbias_group = a->rowbias_group > 0 ? a->rowbias_group : 1;
+  kp.rowbias_ld = a->rowbias_ld;
+  kp.residual = reinterpret_cast<const __half*>(a->residual);
+  kp.res_ld = a->res_ld;
+  const long long m_tiles_ll = (long long)kp.tiles_w * kp.tiles_h * kp.tiles_g;
+  IVV_REQUIRE(m_tiles_ll <= 65535, "ivv_gemm: too many M tiles (%lld)", m_tiles_ll);
+  const int m_tiles = (int)m_tiles_ll;
+
+  // ---- tile-N choice: least padding first, then enough CTAs to fill 148 SMs ----
+  int bn_sel;
+  if (a->geglu) {
+    bn_sel = 128;
+  } else {
+    const int cands[5] = {256, 160, 128, 64, 32};
+    double best_waste = 1e9;
+    for (int i = 0; i < 5; ++i) {
+      const int tiles = (int)((a->n_out + cands[i] - 1) / cands[i]);
+      best_waste = std::min(best_waste, (double)tiles * cands[i] / (double)a->n_out);
+    }
+    bn_sel = -1;
+    int fallback = -1;
+    long long fallback_ctas = -1;
+    for (int i = 0; i < 5; ++i) {
+      const int tiles = (int)((a->n_out + cands[i] - 1) / cands[i]);
+      const double waste = (double)tiles * cands[i] / (double)a->n_out;
+      if (waste > best_waste * 1.07) continue;
+      const long long ctas = (long long)tiles * m_tiles;
+      if (ctas >= 148 && bn_sel < 0) bn_sel = cands[i];
+      if (ctas > fallback_ctas && cands[i] >= 64) {
+        fallback_ctas = ctas;
+        fallback = cands[i];
+      }
+      if (fallback < 0) fallback = cands[i];
+    }
+    if (bn_sel < 0) bn_sel = fallback;
+  }
+  const int n_tiles = (int)((a->n_out + bn_sel - 1) / bn_sel);
+
+  // ---- tensor maps ----
+  CUtensorMap tmA, tmB;
+  {
+    const uint64_t dims[4] = {(uint64_t)a->c, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n_img};
+    const uint64_t strides[4] = {2, (uint64_t)a->a_ld * 2, (uint64_t)a->a_ld * 2 * a->w,
+                                 (uint64_t)a->a_ld * 2 * a->w * a->h};
+    const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)kp.bw, (uint32_t)kp.bh, (uint32_t)kp.bn};
+    if (int rc = make_tmap_f16(&tmA, a->a, 4, dims, strides, box, true)) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)a->c, (uint64_t)a->n_out, (uint64_t)a->taps};
+    const uint64_t strides[3] = {2, (uint64_t)a->w_ld * 2, (uint64_t)a->w_ld * 2 * a->n_out};
+    const uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)bn_sel, 1};
+    if (int rc = make_tmap_f16(&tmB, a->wgt, 3, dims, strides, box, true)) return rc;
+  }
+
+  switch (bn_sel) {
+    case 256: return launch<256, 4>(tmA, tmB, kp, m_tiles, n_tiles, stream);
+    case 160: return launch<160, 3>(tmA, tmB, kp, m_tiles, n_tiles, stream);
+    case 128: return launch<128, 3>(tmA, tmB, kp, m_tiles, n_tiles, stream);
+    case 64: return launch<64, 4>(tmA, tmB, kp, m_tiles, n_tiles, stream);
+    default: return launch<32, 4>(tmA, tmB, kp, m_tiles, n_tiles, stream);
+  }
+}

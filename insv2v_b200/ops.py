@@ -1,0 +1,334 @@
+"""Tensor-level wrappers over the C ABI (include/ivv.h). PyTorch is plumbing only: it owns device memory and the
+stream; every operation below is one call into libivv_b200.so. No CPU or eager-PyTorch fallback exists."""
+import ctypes
+
+import torch
+
+from . import lib as _lib
+
+F16 = torch.float16
+
+
+def _s():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _chk16(t, name):
+    if t is None:
+        return
+    if not t.is_cuda or t.dtype != F16 or not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous CUDA fp16 tensor, got {t.dtype} {t.device} "
+                         f"contiguous={t.is_contiguous()}")
+
+
+def _count():
+    _lib.LAUNCH_COUNT += 1
+
+
+# default allocator; UNet/VAE runners swap in an arena so that CUDA-graph replays see stable addresses
+class Alloc:
+    fn = staticmethod(lambda shape, dtype, device: torch.empty(shape, dtype=dtype, device=device))
+
+
+def empty(shape, dtype, device):
+    return Alloc.fn(tuple(shape), dtype, device)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# weight packing (done once at load time)
+# ----------------------------------------------------------------------------------------------------------------
+def _pad_last(t, mult=8):
+    k = t.shape[-1]
+    kp = (k + mult - 1) // mult * mult
+    if kp == k:
+        return t.contiguous()
+    out = t.new_zeros(*t.shape[:-1], kp)
+    out[..., :k] = t
+    return out
+
+
+def pack_linear(w):
+    """nn.Linear / 1x1-conv weight [out, in(,1,1)] -> fp16 [1, out, in_pad8] (K-major rows, as tcgen05 wants B)."""
+    w = w.reshape(w.shape[0], -1)
+    return _pad_last(w.to(F16)).unsqueeze(0).contiguous()
+
+
+def pack_conv3x3(w):
+    """Conv2d weight [co, ci, 3, 3] -> fp16 [9, co, ci_pad8] (tap-major: tap = ky*3+kx)."""
+    co, ci = w.shape[0], w.shape[1]
+    return _pad_last(w.to(F16).permute(2, 3, 0, 1).reshape(9, co, ci)).contiguous()
+
+
+def pack_conv3x3_im2col(w):
+    """Conv2d weight [co, ci, 3, 3] -> fp16 [1, co, 9*ci] matching ivv_im2col_s2's column order (tap*ci + c)."""
+    co, ci = w.shape[0], w.shape[1]
+    return w.to(F16).permute(0, 2, 3, 1).reshape(1, co, 9 * ci).contiguous()
+
+
+def pack_geglu(w, b):
+    """GEGLU proj weight [2*inner, c] (rows: hidden | gate) -> 128-row tiles [64 hidden | 64 gate] so that one
+    tcgen05 accumulator tile holds both halves of the same 64 output columns; bias permuted identically."""
+    inner = w.shape[0] // 2
+    if inner % 64 != 0:
+        raise ValueError(f"GEGLU inner dim {inner} must be a multiple of 64")
+    idx = torch.arange(inner, device=w.device).reshape(inner // 64, 64)
+    perm = torch.cat([idx, idx + inner], dim=1).reshape(-1)
+    return pack_linear(w[perm]), b[perm].to(F16).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GEMM / conv
+# ----------------------------------------------------------------------------------------------------------------
+def gemm(a, wgt, *, n_img, h, w, c, n_out=None, taps=1, a_ld=None, bias=None, rowbias=None, rowbias_group=0,
+         residual=None, geglu=False, out=None, out_f32=False):
+    """D = conv/linear(A, W) with fused epilogue; A rows are pixels [n_img*h*w, a_ld], W packed by pack_*()."""
+    _chk16(a, "a"), _chk16(wgt, "wgt"), _chk16(bias, "bias"), _chk16(rowbias, "rowbias"), _chk16(residual, "residual")
+    if wgt.dim() != 3 or wgt.shape[0] != taps:
+        raise ValueError(f"weight must be [taps={taps}, n_out, k_pad], got {tuple(wgt.shape)}")
+    n_out = wgt.shape[1] if n_out is None else n_out
+    a_ld = a.shape[-1] if a_ld is None else a_ld
+    rows = n_img * h * w
+    cols = n_out // 2 if geglu else n_out
+    if out is None:
+        out = empty((rows, cols), torch.float32 if out_f32 else F16, a.device)
+    args = _lib.GemmArgs()
+    args.a, args.n_img, args.h, args.w, args.c, args.a_ld = a.data_ptr(), n_img, h, w, c, a_ld
+    args.wgt, args.n_out, args.w_ld = wgt.data_ptr(), n_out, wgt.shape[2]
+    args.taps, args.geglu = taps, int(geglu)
+    args.d, args.d_ld, args.out_f32 = out.data_ptr(), out.shape[-1], int(out.dtype == torch.float32)
+    args.bias = bias.data_ptr() if bias is not None else None
+    if rowbias is not None:
+        args.rowbias, args.rowbias_group, args.rowbias_ld = rowbias.data_ptr(), rowbias_group, rowbias.shape[-1]
+    if residual is not None:
+        args.residual, args.res_ld = residual.data_ptr(), residual.shape[-1]
+    _lib.check(_lib.load().ivv_gemm(ctypes.byref(args), _s()), "ivv_gemm")
+    _count()
+    return out
+
+
+def linear(x, wgt, bias=None, residual=None, geglu=False, out=None):
+    """x [rows, k] -> [rows, n_out] (nn.Linear semantics)."""
+    rows, k = x.shape
+    return gemm(x, wgt, n_img=1, h=1, w=rows, c=k, bias=bias, residual=residual, geglu=geglu, out=out)
+
+
+def conv3x3(x, wgt, n_img, h, w, bias=None, rowbias=None, rowbias_group=0, residual=None, out=None, out_f32=False):
+    """x frames [n_img*h*w, c] -> [n_img*h*w, co]; stride 1, zero pad 1 (InflatedConv3d, resnet.py:10-18)."""
+    return gemm(x, wgt, n_img=n_img, h=h, w=w, c=x.shape[-1], taps=9, bias=bias, rowbias=rowbias,
+                rowbias_group=rowbias_group, residual=residual, out=out, out_f32=out_f32)
+
+
+def conv3x3_s2(x, wgt_im2col, n_img, h, w, bias=None):
+    """stride-2 3x3 conv, pad 1 (Downsample3D, resnet.py:99-107): im2col gather then one tcgen05 GEMM."""
+    _chk16(x, "x")
+    c = x.shape[-1]
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    cols = empty((n_img * ho * wo, 9 * c), F16, x.device)
+    _lib.check(_lib.load().ivv_im2col_s2(_p(x), _p(cols), n_img, h, w, c, ho, wo, _s()), "ivv_im2col_s2")
+    _count()
+    return gemm(cols, wgt_im2col, n_img=1, h=1, w=n_img * ho * wo, c=9 * c, bias=bias), ho, wo
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# normalisation
+# ----------------------------------------------------------------------------------------------------------------
+_ws_cache = {}
+
+
+def _gn_ws(nbytes, device):
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def groupnorm(x, gamma, beta, n_img, hw, groups, frames_per_group, eps, silu, out=None):
+    """x frames [n_img*hw, c]; statistics span frames_per_group consecutive frames (5-D GroupNorm of
+    ResnetBlock3D, resnet.py:177) or one frame (frames_per_group=1: attention.py:101)."""
+    _chk16(x, "x"), _chk16(gamma, "gamma"), _chk16(beta, "beta")
+    c = x.shape[-1]
+    if out is None:
+        out = empty(x.shape, F16, x.device)
+    L = _lib.load()
+    need = L.ivv_groupnorm_ws_bytes(n_img, groups, frames_per_group)
+    ws = _gn_ws(need, x.device)
+    _lib.check(L.ivv_groupnorm(_p(x), _p(out), _p(gamma), _p(beta), n_img, hw, c, groups, frames_per_group,
+                               float(eps), int(silu), _p(ws), ws.numel(), _s()), "ivv_groupnorm")
+    _lib.LAUNCH_COUNT += 2
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, pe=None, rows_per_frame=0, frames=0, pe_start=0, out=None):
+    _chk16(x, "x"), _chk16(gamma, "gamma"), _chk16(beta, "beta")
+    rows, c = x.shape
+    if out is None:
+        out = empty(x.shape, F16, x.device)
+    if pe is not None and (pe.dtype != torch.float32 or not pe.is_contiguous()):
+        raise ValueError("pe must be contiguous fp32")
+    _lib.check(_lib.load().ivv_layernorm(_p(x), _p(out), _p(gamma), _p(beta), rows, c, float(eps), _p(pe),
+                                         rows_per_frame, frames, pe_start, _s()), "ivv_layernorm")
+    _count()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# attention
+# ----------------------------------------------------------------------------------------------------------------
+def attention(q, k, v, *, n_batch, s_q, s_kv, heads, d, q_ld, kv_ld, kv_div=1, scale=None, out=None):
+    """softmax(q k^T * scale) v per (batch, head). q/k/v may be column slices of wider row-major buffers
+    (pass the buffer's row stride as q_ld / kv_ld)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        if not t.is_cuda or t.dtype != F16:
+            raise ValueError(f"{n}: expected CUDA fp16")
+    scale = d ** -0.5 if scale is None else scale
+    if out is None:
+        out = empty((n_batch * s_q, heads * d), F16, q.device)
+    _lib.check(_lib.load().ivv_attention(_p(q), q_ld, _p(k), _p(v), kv_ld, _p(out), out.shape[-1], n_batch, s_q, s_kv,
+                                         kv_div, heads, d, float(scale), _s()), "ivv_attention")
+    _count()
+    return out
+
+
+def temporal_attention(qkv, clips, frames, hw, c, heads, scale=None, out=None):
+    _chk16(qkv, "qkv")
+    scale = (c // heads) ** -0.5 if scale is None else scale
+    if out is None:
+        out = empty((clips * frames * hw, c), F16, qkv.device)
+    _lib.check(_lib.load().ivv_temporal_attention(_p(qkv), _p(out), clips, frames, hw, c, heads, float(scale), _s()),
+               "ivv_temporal_attention")
+    _count()
+    return out
+
+
+def softmax_rows(x, scale, out=None):
+    _chk16(x, "x")
+    rows, cols = x.shape
+    if out is None:
+        out = empty(x.shape, F16, x.device)
+    _lib.check(_lib.load().ivv_softmax_rows(_p(x), _p(out), rows, cols, float(scale), _s()), "ivv_softmax_rows")
+    _count()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# data movement / elementwise
+# ----------------------------------------------------------------------------------------------------------------
+def upsample_nearest(x, n_img, h, w, ho=None, wo=None):
+    _chk16(x, "x")
+    c = x.shape[-1]
+    ho, wo = (2 * h if ho is None else ho), (2 * w if wo is None else wo)
+    out = empty((n_img * ho * wo, c), F16, x.device)
+    _lib.check(_lib.load().ivv_upsample_nearest(_p(x), _p(out), n_img, h, w, c, ho, wo, _s()), "ivv_upsample_nearest")
+    _count()
+    return out, ho, wo
+
+
+def concat_channels(a, b):
+    _chk16(a, "a"), _chk16(b, "b")
+    rows = a.shape[0]
+    out = empty((rows, a.shape[1] + b.shape[1]), F16, a.device)
+    _lib.check(_lib.load().ivv_concat_channels(_p(a), a.shape[1], _p(b), b.shape[1], _p(out), rows, _s()),
+               "ivv_concat_channels")
+    _count()
+    return out
+
+
+def ncfhw_to_frames(x, c_pad):
+    """[b, c, f, h, w] fp32/fp16 -> frames [b*f*h*w, c_pad] fp16 (the reference's `(b f)` fold made physical once)."""
+    if x.dtype not in (torch.float32, F16) or not x.is_cuda:
+        raise ValueError("ncfhw_to_frames: expected CUDA fp32/fp16")
+    x = x.contiguous()
+    b, c, f, h, w = x.shape
+    out = empty((b * f * h * w, c_pad), F16, x.device)
+    _lib.check(_lib.load().ivv_ncfhw_to_frames(_p(x), int(x.dtype == torch.float32), _p(out), b, c, f, h * w, c_pad,
+                                               _s()), "ivv_ncfhw_to_frames")
+    _count()
+    return out
+
+
+def frames_to_ncfhw(x, b, c, f, h, w, out_dtype=torch.float32):
+    if x.dtype not in (torch.float32, F16) or not x.is_contiguous():
+        raise ValueError("frames_to_ncfhw: expected contiguous fp32/fp16")
+    out = torch.empty((b, c, f, h, w), dtype=out_dtype, device=x.device)
+    _lib.check(_lib.load().ivv_frames_to_ncfhw(_p(x), int(x.dtype == torch.float32), x.shape[-1], _p(out),
+                                               int(out_dtype == torch.float32), b, c, f, h * w, _s()),
+               "ivv_frames_to_ncfhw")
+    _count()
+    return out
+
+
+def timestep_embedding(t, dim, flip_sin_to_cos=True, freq_shift=0.0):
+    t = t.to(torch.float32).contiguous()
+    out = empty((t.shape[0], dim), F16, t.device)
+    _lib.check(_lib.load().ivv_timestep_embedding(_p(t), _p(out), t.shape[0], dim, int(flip_sin_to_cos),
+                                                  float(freq_shift), _s()), "ivv_timestep_embedding")
+    _count()
+    return out
+
+
+def silu(x):
+    _chk16(x, "x")
+    out = empty(x.shape, F16, x.device)
+    _lib.check(_lib.load().ivv_silu(_p(x), _p(out), x.numel(), _s()), "ivv_silu")
+    _count()
+    return out
+
+
+def scale(x, a, b=0.0):
+    _chk16(x, "x")
+    out = empty(x.shape, F16, x.device)
+    _lib.check(_lib.load().ivv_scale(_p(x), _p(out), x.numel(), float(a), float(b), _s()), "ivv_scale")
+    _count()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# flow warp / sampler step
+# ----------------------------------------------------------------------------------------------------------------
+def _chk32(t, name):
+    if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous CUDA fp32 tensor")
+
+
+def warp_image_f32(image, flow):
+    _chk32(image, "image"), _chk32(flow, "flow")
+    n, c, h, w = image.shape
+    out = torch.empty_like(image)
+    _lib.check(_lib.load().ivv_warp_image(_p(image), _p(flow), _p(out), n, c, h, w, _s()), "ivv_warp_image")
+    _count()
+    return out
+
+
+def resize_flow_f32(flow, ho, wo):
+    _chk32(flow, "flow")
+    n, _, h, w = flow.shape
+    out = torch.empty((n, 2, ho, wo), dtype=torch.float32, device=flow.device)
+    _lib.check(_lib.load().ivv_resize_flow(_p(flow), _p(out), n, h, w, ho, wo, _s()), "ivv_resize_flow")
+    _count()
+    return out
+
+
+def flow_noise_correction_(eps, delta_ref, flow_lat):
+    """eps [Q, C, h, w] += masked mean over R reference frames of warp(delta_ref[r], flow_lat[q, r]) — in place."""
+    _chk32(eps, "eps"), _chk32(delta_ref, "delta_ref"), _chk32(flow_lat, "flow_lat")
+    q, c, h, w = eps.shape
+    r = delta_ref.shape[0]
+    _lib.check(_lib.load().ivv_flow_noise_correction(_p(delta_ref), _p(flow_lat), _p(eps), q, r, c, h, w, _s()),
+               "ivv_flow_noise_correction")
+    _count()
+    return eps
+
+
+def cfg_ddim_step_(eps3, latent, text_cfg, img_cfg, alpha_t, alpha_prev, eps_out=None):
+    _chk32(eps3, "eps3"), _chk32(latent, "latent")
+    n = latent.numel()
+    _lib.check(_lib.load().ivv_cfg_ddim_step(_p(eps3), _p(latent), _p(eps_out), n, float(text_cfg), float(img_cfg),
+                                             float(alpha_t), float(alpha_prev), _s()), "ivv_cfg_ddim_step")
+    _count()
+    return latent

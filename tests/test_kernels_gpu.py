@@ -1,0 +1,335 @@
+"""Per-kernel parity on the GPU: every C-ABI entry point against a plain PyTorch fp32 statement of the same op
+(the op-level definitions are the ones oracle/insv2v_oracle.py uses; tolerances are written next to each check).
+Run with `pytest -m gpu`."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-3, 1e-4  # BASELINE.json north_star: rtol=1e-3 / atol=1e-4 (fp16 outputs)
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _setup():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    from insv2v_b200 import lib
+    lib.load()
+    yield
+
+
+def _ops():
+    from insv2v_b200 import ops
+    return ops
+
+
+def report(name, got, ref, rtol=RTOL, atol=ATOL, frac_ok=1.0):
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = (err > tol).float().mean().item()
+    print(f"[{name}] max_abs={err.max().item():.3e} max_ref={ref.abs().max().item():.3e} "
+          f"viol_frac={bad:.3e} mean_abs={err.mean().item():.3e}")
+    assert torch.isfinite(got).all(), f"{name}: non-finite output"
+    assert bad <= 1.0 - frac_ok, f"{name}: {bad:.3e} of elements outside rtol={rtol} atol={atol}"
+
+
+def h16(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, device="cuda", generator=g) * scale).half()
+
+
+# ------------------------------------------------------------------------------------------------ GEMM / linear
+@pytest.mark.parametrize("rows,k,n", [(128, 64, 128), (300, 320, 320), (1000, 1280, 640), (77 * 3, 768, 2560),
+                                      (3, 320, 1280), (4608, 2560, 1280), (130, 72, 40)])
+def test_linear(rows, k, n):
+    ops = _ops()
+    x = h16(rows, k, seed=1)
+    w = h16(n, k, scale=k ** -0.5, seed=2)
+    b = h16(n, seed=3)
+    res = h16(rows, n, seed=4)
+    out = ops.linear(x, ops.pack_linear(w), bias=b, residual=res)
+    ref = x.float() @ w.float().t() + b.float() + res.float()
+    report(f"linear {rows}x{k}x{n}", out, ref)
+
+
+def test_linear_geglu():
+    ops = _ops()
+    rows, c = 500, 320
+    x = h16(rows, c, seed=1)
+    w = h16(8 * c, c, scale=c ** -0.5, seed=2)
+    b = h16(8 * c, scale=0.1, seed=3)
+    wp, bp = ops.pack_geglu(w, b)
+    out = ops.linear(x, wp, bias=bp, geglu=True)
+    y = x.float() @ w.float().t() + b.float()
+    hid, gate = y.chunk(2, dim=-1)
+    ref = hid * F.gelu(gate)
+    assert out.shape == (rows, 4 * c)
+    report("geglu", out, ref)
+
+
+def test_linear_out_f32_and_rowbias():
+    ops = _ops()
+    rows, k, n = 2 * 4 * 24, 128, 72
+    x = h16(rows, k, seed=1)
+    w = h16(n, k, scale=k ** -0.5, seed=2)
+    rb = h16(2, n, seed=5)
+    out = ops.gemm(x, ops.pack_linear(w), n_img=1, h=1, w=rows, c=k, rowbias=rb, rowbias_group=rows // 2,
+                   out_f32=True)
+    ref = x.float() @ w.float().t() + rb.float().repeat_interleave(rows // 2, dim=0)
+    assert out.dtype == torch.float32
+    report("linear f32+rowbias", out, ref, rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ conv
+def _frames(x_nchw):
+    n, c, h, w = x_nchw.shape
+    return x_nchw.permute(0, 2, 3, 1).reshape(n * h * w, c).contiguous()
+
+
+def _nchw(fr, n, h, w):
+    return fr.reshape(n, h, w, -1).permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("n,ci,co,h,w", [(2, 64, 64, 16, 16), (6, 320, 320, 32, 48), (4, 8, 320, 32, 48),
+                                         (5, 640, 1280, 8, 12), (48, 1280, 1280, 4, 6), (3, 128, 8, 12, 20),
+                                         (2, 192, 320, 5, 7)])
+def test_conv3x3(n, ci, co, h, w):
+    ops = _ops()
+    x = h16(n, ci, h, w, seed=1)
+    wt = h16(co, ci, 3, 3, scale=(9 * ci) ** -0.5, seed=2)
+    b = h16(co, seed=3)
+    out = ops.conv3x3(_frames(x), ops.pack_conv3x3(wt), n, h, w, bias=b)
+    ref = F.conv2d(x.float(), wt.float(), b.float(), padding=1)
+    report(f"conv3x3 n{n} {ci}->{co} {h}x{w}", _nchw(out, n, h, w), ref)
+
+
+def test_conv3x3_fused_temb_residual():
+    ops = _ops()
+    b_, f, ci, co, h, w = 2, 4, 128, 192, 8, 12
+    n = b_ * f
+    x = h16(n, ci, h, w, seed=1)
+    wt = h16(co, ci, 3, 3, scale=(9 * ci) ** -0.5, seed=2)
+    bias = h16(co, seed=3)
+    temb = h16(b_, co, seed=4)
+    res = h16(n, co, h, w, seed=5)
+    out = ops.conv3x3(_frames(x), ops.pack_conv3x3(wt), n, h, w, bias=bias, rowbias=temb, rowbias_group=f * h * w,
+                      residual=_frames(res))
+    ref = F.conv2d(x.float(), wt.float(), bias.float(), padding=1)
+    ref = ref + temb.float().repeat_interleave(f, dim=0)[:, :, None, None] + res.float()
+    report("conv3x3+temb+res", _nchw(out, n, h, w), ref)
+
+
+@pytest.mark.parametrize("n,c,co,h,w", [(4, 320, 320, 32, 48), (3, 64, 128, 9, 13)])
+def test_conv3x3_stride2(n, c, co, h, w):
+    ops = _ops()
+    x = h16(n, c, h, w, seed=1)
+    wt = h16(co, c, 3, 3, scale=(9 * c) ** -0.5, seed=2)
+    b = h16(co, seed=3)
+    out, ho, wo = ops.conv3x3_s2(_frames(x), ops.pack_conv3x3_im2col(wt), n, h, w, bias=b)
+    ref = F.conv2d(x.float(), wt.float(), b.float(), stride=2, padding=1)
+    assert (ho, wo) == tuple(ref.shape[-2:])
+    report("conv3x3 s2", _nchw(out, n, ho, wo), ref)
+
+
+# ------------------------------------------------------------------------------------------------ norms
+@pytest.mark.parametrize("b,f,c,h,w,fpg,silu", [(3, 16, 320, 32, 48, 16, True), (2, 4, 640, 8, 12, 1, False),
+                                                (1, 2, 2560, 4, 6, 2, True), (2, 3, 128, 5, 7, 3, True),
+                                                (1, 4, 512, 16, 16, 1, True)])
+def test_groupnorm(b, f, c, h, w, fpg, silu):
+    ops = _ops()
+    x = (h16(b * f, c, h, w, seed=1).float() * 1.5 + 0.3).half()
+    g = h16(c, seed=2)
+    be = h16(c, seed=3)
+    eps = 1e-5
+    out = ops.groupnorm(_frames(x), g, be, b * f, h * w, 32, fpg, eps, silu)
+    # frames_per_group frames share statistics: reshape to [groups_of_frames, c, fpg, h, w]
+    x5 = x.float().reshape(b * f // fpg, fpg, c, h, w).permute(0, 2, 1, 3, 4)
+    ref = F.group_norm(x5, 32, g.float(), be.float(), eps)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
+    report(f"groupnorm c{c} fpg{fpg}", _nchw(out, b * f, h, w), ref, rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("rows,c", [(1000, 320), (77, 640), (4608, 1280)])
+def test_layernorm(rows, c):
+    ops = _ops()
+    x = h16(rows, c, seed=1)
+    g, be = h16(c, seed=2), h16(c, seed=3)
+    out = ops.layernorm(x, g, be)
+    ref = F.layer_norm(x.float(), (c,), g.float(), be.float(), 1e-5)
+    report(f"layernorm {rows}x{c}", out, ref, rtol=1e-3, atol=1e-3)
+
+
+def test_layernorm_pe():
+    ops = _ops()
+    clips, frames, hw, c = 2, 8, 24, 320
+    x = h16(clips * frames * hw, c, seed=1)
+    g, be = h16(c, seed=2), h16(c, seed=3)
+    pe = torch.randn(32, c, device="cuda")
+    out = ops.layernorm(x, g, be, pe=pe, rows_per_frame=hw, frames=frames, pe_start=3)
+    ref = F.layer_norm(x.float(), (c,), g.float(), be.float(), 1e-5).reshape(clips, frames, hw, c)
+    ref = ref + pe[3:3 + frames][None, :, None, :]
+    report("layernorm+pe", out, ref.reshape(-1, c), rtol=1e-3, atol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------ attention
+def _sdpa_ref(q, k, v, heads):
+    # q [n, sq, h*d], k/v [n, skv, h*d] fp32
+    n, sq, c = q.shape
+    d = c // heads
+    qh = q.reshape(n, sq, heads, d).transpose(1, 2)
+    kh = k.reshape(n, -1, heads, d).transpose(1, 2)
+    vh = v.reshape(n, -1, heads, d).transpose(1, 2)
+    p = torch.softmax(qh @ kh.transpose(-1, -2) * d ** -0.5, dim=-1)
+    return (p @ vh).transpose(1, 2).reshape(n, sq, c)
+
+
+@pytest.mark.parametrize("n,s,heads,d", [(2, 128, 2, 64), (3, 1536, 8, 40), (4, 384, 8, 80), (6, 96, 8, 160),
+                                         (5, 24, 8, 160), (2, 200, 4, 40)])
+def test_self_attention(n, s, heads, d):
+    ops = _ops()
+    c = heads * d
+    qkv = h16(n * s, 3 * c, seed=1)
+    out = ops.attention(qkv[:, :c], qkv[:, c:2 * c], qkv[:, 2 * c:], n_batch=n, s_q=s, s_kv=s, heads=heads, d=d,
+                        q_ld=3 * c, kv_ld=3 * c)
+    q, k, v = (t.float().reshape(n, s, c) for t in qkv.chunk(3, dim=-1))
+    ref = _sdpa_ref(q, k, v, heads)
+    # P is rounded to fp16 before the PV product (as in every fp16 tensor-core flash attention, incl. the reference's
+    # xformers/SDPA path): allow 2e-3 relative + 5e-4 absolute against the fp32 truth.
+    report(f"self-attn n{n} s{s} h{heads} d{d}", out.reshape(n, s, c), ref, rtol=2e-3, atol=5e-4)
+
+
+@pytest.mark.parametrize("clips,frames,s,heads,d", [(3, 4, 384, 8, 80), (2, 3, 1536, 8, 40), (2, 2, 24, 8, 160)])
+def test_cross_attention(clips, frames, s, heads, d):
+    ops = _ops()
+    c = heads * d
+    n = clips * frames
+    q = h16(n * s, c, seed=1)
+    kv = h16(clips * 77, 2 * c, seed=2)
+    out = ops.attention(q, kv[:, :c], kv[:, c:], n_batch=n, s_q=s, s_kv=77, heads=heads, d=d, q_ld=c, kv_ld=2 * c,
+                        kv_div=frames)
+    k, v = (t.float().reshape(clips, 77, c).repeat_interleave(frames, dim=0) for t in kv.chunk(2, dim=-1))
+    ref = _sdpa_ref(q.float().reshape(n, s, c), k, v, heads)
+    report(f"cross-attn s{s} d{d}", out.reshape(n, s, c), ref, rtol=2e-3, atol=5e-4)
+
+
+@pytest.mark.parametrize("clips,frames,hw,heads,d", [(3, 16, 96, 8, 40), (2, 16, 24, 8, 160), (1, 5, 35, 8, 80),
+                                                     (1, 32, 6, 8, 160)])
+def test_temporal_attention(clips, frames, hw, heads, d):
+    ops = _ops()
+    c = heads * d
+    qkv = h16(clips * frames * hw, 3 * c, seed=1)
+    out = ops.temporal_attention(qkv, clips, frames, hw, c, heads)
+    t = qkv.float().reshape(clips, frames, hw, 3 * c).permute(0, 2, 1, 3).reshape(clips * hw, frames, 3 * c)
+    q, k, v = t.chunk(3, dim=-1)
+    ref = _sdpa_ref(q, k, v, heads).reshape(clips, hw, frames, c).permute(0, 2, 1, 3).reshape(-1, c)
+    report(f"temporal-attn f{frames} d{d}", out, ref)
+
+
+def test_softmax_rows():
+    ops = _ops()
+    x = h16(300, 1536, scale=3.0, seed=1)
+    out = ops.softmax_rows(x, 0.5)
+    report("softmax_rows", out, torch.softmax(x.float() * 0.5, dim=-1), rtol=1e-3, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ glue
+def test_layout_roundtrip_and_glue():
+    ops = _ops()
+    x = torch.randn(2, 5, 3, 6, 7, device="cuda")
+    fr = ops.ncfhw_to_frames(x, 8)
+    assert fr.shape == (2 * 3 * 42, 8)
+    ref = x.permute(0, 2, 3, 4, 1).reshape(-1, 5)
+    assert torch.equal(fr[:, :5], ref.half()) and (fr[:, 5:] == 0).all()
+    back = ops.frames_to_ncfhw(fr, 2, 5, 3, 6, 7)
+    assert torch.equal(back, x.half().float())
+    a, b = h16(100, 64, seed=1), h16(100, 128, seed=2)
+    assert torch.equal(ops.concat_channels(a, b), torch.cat([a, b], dim=1))
+    img = h16(3, 64, 5, 7, seed=3)
+    up, ho, wo = ops.upsample_nearest(_frames(img), 3, 5, 7)
+    assert torch.equal(_nchw(up, 3, ho, wo), F.interpolate(img.float(), scale_factor=2.0, mode="nearest").half())
+    up2, ho, wo = ops.upsample_nearest(_frames(img), 3, 5, 7, 9, 15)
+    assert torch.equal(_nchw(up2, 3, 9, 15), F.interpolate(img.float(), size=(9, 15), mode="nearest").half())
+    report("silu", ops.silu(a), F.silu(a.float()))
+    report("scale", ops.scale(a, 1 / 0.18215), a.float() / 0.18215)
+
+
+def test_timestep_embedding():
+    ops = _ops()
+    t = torch.tensor([981.0, 1.0, 500.0], device="cuda")
+    out = ops.timestep_embedding(t, 320)
+    half = 160
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, device="cuda", dtype=torch.float32) / half)
+    arg = t[:, None] * freqs[None]
+    ref = torch.cat([torch.cos(arg), torch.sin(arg)], dim=-1)
+    report("timestep", out, ref, rtol=1e-3, atol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------ flow warp
+def _warp_ref(image, flow):
+    n, c, h, w = image.shape
+    ys, xs = torch.meshgrid(torch.arange(h, device=image.device), torch.arange(w, device=image.device), indexing="ij")
+    grid = torch.stack([xs, ys], dim=-1).float()[None].repeat(n, 1, 1, 1) + flow.permute(0, 2, 3, 1)
+    grid[..., 0] = 2 * (grid[..., 0] / (w - 1) - 0.5)
+    grid[..., 1] = 2 * (grid[..., 1] / (h - 1) - 0.5)
+    return F.grid_sample(image, grid, mode="bilinear", align_corners=True)
+
+
+def test_warp_and_resize_flow():
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    img = torch.randn(4, 4, 32, 48, device="cuda", generator=g)
+    flow = torch.randn(4, 2, 32, 48, device="cuda", generator=g) * 6
+    report("warp_image", ops.warp_image_f32(img, flow), _warp_ref(img, flow), rtol=1e-4, atol=1e-4)
+    big = torch.randn(4, 2, 256, 384, device="cuda", generator=g) * 5
+    scaled = big.clone()
+    scaled[:, 0] *= 48 / 384
+    scaled[:, 1] *= 32 / 256
+    ref = F.interpolate(scaled, size=(32, 48), mode="bilinear", align_corners=False)
+    report("resize_flow /8", ops.resize_flow_f32(big, 32, 48), ref, rtol=1e-5, atol=1e-5)
+    ref2 = F.interpolate(big[:, :, :100, :90] * 1.0, size=(37, 53), mode="bilinear", align_corners=False)
+    b2 = big[:, :, :100, :90].contiguous()
+    got2 = ops.resize_flow_f32(b2, 37, 53)
+    ref2[:, 0] *= 1.0
+    s = b2.clone()
+    s[:, 0] *= 53 / 90
+    s[:, 1] *= 37 / 100
+    report("resize_flow general", got2, F.interpolate(s, size=(37, 53), mode="bilinear", align_corners=False),
+           rtol=1e-5, atol=1e-5)
+
+
+def test_flow_noise_correction():
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    Q, R, C, h, w = 12, 4, 4, 32, 48
+    delta = torch.randn(R, C, h, w, device="cuda", generator=g)
+    flow = torch.randn(Q, R, 2, h, w, device="cuda", generator=g) * 8
+    eps = torch.randn(Q, C, h, w, device="cuda", generator=g)
+    ref = eps.clone()
+    for q in range(Q):
+        wd = _warp_ref(delta, flow[q])
+        m = _warp_ref(torch.ones_like(delta[:, :1]), flow[q])
+        msum = m.sum(dim=0, keepdim=True)
+        corr = torch.where(msum > 0.5, wd.sum(dim=0, keepdim=True) / msum, torch.zeros_like(msum))
+        ref[q:q + 1] += torch.where(msum > 0.5, corr, torch.zeros_like(corr))
+    got = ops.flow_noise_correction_(eps.clone(), delta, flow)
+    report("flow_noise_correction", got, ref, rtol=1e-4, atol=1e-4, frac_ok=0.9999)
+
+
+def test_cfg_ddim_step():
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    eps3 = torch.randn(3, 1000, device="cuda", generator=g)
+    lat = torch.randn(1000, device="cuda", generator=g)
+    at, ap = 0.31, 0.42
+    e = eps3[0] + 1.5 * (eps3[1] - eps3[0]) + 7.5 * (eps3[2] - eps3[1])
+    x0 = (lat - (1 - at) ** 0.5 * e) / at ** 0.5
+    ref = ap ** 0.5 * x0 + (1 - ap) ** 0.5 * e
+    got = ops.cfg_ddim_step_(eps3, lat.clone(), 7.5, 1.5, at, ap)
+    report("cfg_ddim", got, ref, rtol=1e-5, atol=1e-5)
