@@ -104,7 +104,7 @@ def test_conv3x3(n, ci, co, h, w):
     wt = h16(co, ci, 3, 3, scale=(9 * ci) ** -0.5, seed=2)
     b = h16(co, seed=3)
     out = ops.conv3x3(_frames(x), ops.pack_conv3x3(wt), n, h, w, bias=b)
-    ref = F.conv2d(x.float(), wt.float(), b.float(), padding=1)
+    ref = F.conv2d(x.double(), wt.double(), b.double(), padding=1)  # fp64: no reference-side rounding
     report(f"conv3x3 n{n} {ci}->{co} {h}x{w}", _nchw(out, n, h, w), ref)
 
 
