@@ -52,9 +52,11 @@ typedef struct {
 } ivv_gemm_args;
 int ivv_gemm(const ivv_gemm_args* args, ivv_stream_t stream);
 
-/* im2col for the stride-2 3x3 convolutions (Downsample3D, resnet.py:99-107): out[n,ho,wo, tap*c + ci], pad 1.   */
+/* im2col for the stride-2 3x3 convolutions: out[n,ho,wo, tap*c + ci] = x[n, 2ho+ky-pad, 2wo+kx-pad, ci].
+ * pad = 1: Downsample3D (resnet.py:99-107, symmetric pad 1);  pad = 0: the VAE encoder's Downsample
+ * (vqvae/model.py:55-71: zero pad (0,1,0,1) then stride-2 conv) — the missing bottom/right taps read as zero.      */
 int ivv_im2col_s2(const void* x, void* out, int64_t n_img, int64_t h, int64_t w, int64_t c, int64_t ho, int64_t wo,
-                  ivv_stream_t stream);
+                  int32_t pad, ivv_stream_t stream);
 
 /* ---- K6/K7: GroupNorm (+SiLU) ------------------------------------------------------------------------------
  * Replaces torch.nn.GroupNorm + F.silu at resnet.py:177-178,188-194, unet.py:427-428 (5-D: statistics span
@@ -87,8 +89,9 @@ int ivv_attention(const void* q, int64_t q_ld, const void* k, const void* v, int
 int ivv_temporal_attention(const void* qkv, void* o, int64_t clips, int64_t frames, int64_t hw, int64_t c,
                            int32_t heads, float scale, ivv_stream_t stream);
 
-/* ---- row softmax for the materialised VAE attention (vqvae/model.py:183-186) ------------------------------- */
-int ivv_softmax_rows(const void* x, void* y, int64_t rows, int64_t cols, float scale, ivv_stream_t stream);
+/* ---- row softmax for the materialised VAE attention (vqvae/model.py:183-186): x fp32 or fp16 -> y fp16 ------- */
+int ivv_softmax_rows(const void* x, int32_t x_is_f32, void* y, int64_t rows, int64_t cols, float scale,
+                     ivv_stream_t stream);
 
 /* ---- K9 and layout glue -------------------------------------------------------------------------------------*/
 /* nearest 2x upsample of frames (resnet.py:59-61, vqvae/model.py:48): [n,h,w,c] -> [n,2h,2w,c] (or to ho,wo)     */

@@ -5,9 +5,9 @@
 
 namespace ivv {
 
-// out[n, ho, wo, tap*c + ci] = x[n, 2*ho + ky - 1, 2*wo + kx - 1, ci]  (zero outside), tap = ky*3+kx
+// out[n, ho, wo, tap*c + ci] = x[n, 2*ho + ky - pad, 2*wo + kx - pad, ci]  (zero outside), tap = ky*3+kx
 __global__ void im2col_s2_kernel(const __half* __restrict__ x, __half* __restrict__ out, long long n_img, int h, int w,
-                                 int c, int ho, int wo) {
+                                 int c, int ho, int wo, int pad) {
   const int V = c / 8;
   const long long total = n_img * ho * wo * 9 * V;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -20,8 +20,8 @@ __global__ void im2col_s2_kernel(const __half* __restrict__ x, __half* __restric
     t /= wo;
     const int oy = (int)(t % ho);
     const long long n = t / ho;
-    const int iy = 2 * oy + tap / 3 - 1;
-    const int ix = 2 * ox + tap % 3 - 1;
+    const int iy = 2 * oy + tap / 3 - pad;
+    const int ix = 2 * ox + tap % 3 - pad;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (iy >= 0 && iy < h && ix >= 0 && ix < w)
       v = *reinterpret_cast<const uint4*>(x + ((n * h + iy) * w + ix) * c + vec * 8);
@@ -158,13 +158,15 @@ using namespace ivv;
 #define STREAM reinterpret_cast<cudaStream_t>(stream_)
 
 extern "C" int ivv_im2col_s2(const void* x, void* out, int64_t n_img, int64_t h, int64_t w, int64_t c, int64_t ho,
-                             int64_t wo, ivv_stream_t stream_) {
+                             int64_t wo, int32_t pad, ivv_stream_t stream_) {
   IVV_REQUIRE(x && out && n_img > 0 && c % 8 == 0, "ivv_im2col_s2: bad arguments (c must be a multiple of 8)");
-  IVV_REQUIRE(ho == (h - 1) / 2 + 1 && wo == (w - 1) / 2 + 1, "ivv_im2col_s2: output size must be (h-1)/2+1");
+  IVV_REQUIRE(pad == 0 || pad == 1, "ivv_im2col_s2: pad must be 0 (VAE Downsample) or 1 (Downsample3D)");
+  IVV_REQUIRE(ho == (h - 2 + pad) / 2 + 1 && wo == (w - 2 + pad) / 2 + 1,
+              "ivv_im2col_s2: output size must be (h-2+pad)/2+1");
   const long long total = n_img * ho * wo * 9 * (c / 8);
   im2col_s2_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(reinterpret_cast<const __half*>(x),
                                                              reinterpret_cast<__half*>(out), n_img, (int)h, (int)w,
-                                                             (int)c, (int)ho, (int)wo);
+                                                             (int)c, (int)ho, (int)wo, (int)pad);
   IVV_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -183,15 +183,16 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, __half* __restric
 // ------------------------------------------------------------------------------------------------
 // row softmax (VAE mid attention scores): y = softmax(x * scale) per row, fp16 in/out, fp32 math
 // ------------------------------------------------------------------------------------------------
-__global__ void softmax_rows_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long rows, int cols,
+template <typename TIn>
+__global__ void softmax_rows_kernel(const TIn* __restrict__ x, __half* __restrict__ y, long long rows, int cols,
                                     float scale) {
   const long long row = blockIdx.x;
   if (row >= rows) return;
   __shared__ float s_red[32];
-  const __half* xr = x + row * cols;
+  const TIn* xr = x + row * cols;
   __half* yr = y + row * cols;
   float m = -INFINITY;
-  for (int i = threadIdx.x; i < cols; i += blockDim.x) m = fmaxf(m, __half2float(xr[i]) * scale);
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) m = fmaxf(m, (float)xr[i] * scale);
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = m;
   __syncthreads();
@@ -199,7 +200,7 @@ __global__ void softmax_rows_kernel(const __half* __restrict__ x, __half* __rest
   for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, s_red[i]);
   __syncthreads();
   float s = 0.f;
-  for (int i = threadIdx.x; i < cols; i += blockDim.x) s += __expf(__half2float(xr[i]) * scale - m);
+  for (int i = threadIdx.x; i < cols; i += blockDim.x) s += __expf((float)xr[i] * scale - m);
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
   __syncthreads();
@@ -207,7 +208,7 @@ __global__ void softmax_rows_kernel(const __half* __restrict__ x, __half* __rest
   for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += s_red[i];
   const float inv = 1.f / s;
   for (int i = threadIdx.x; i < cols; i += blockDim.x)
-    yr[i] = __float2half_rn(__expf(__half2float(xr[i]) * scale - m) * inv);
+    yr[i] = __float2half_rn(__expf((float)xr[i] * scale - m) * inv);
 }
 
 }  // namespace ivv
@@ -296,13 +297,17 @@ extern "C" int ivv_layernorm(const void* x, void* y, const void* gamma, const vo
   return 0;
 }
 
-extern "C" int ivv_softmax_rows(const void* x, void* y, int64_t rows, int64_t cols, float scale,
+extern "C" int ivv_softmax_rows(const void* x, int32_t x_is_f32, void* y, int64_t rows, int64_t cols, float scale,
                                 ivv_stream_t stream_) {
   using namespace ivv;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   IVV_REQUIRE(x && y && rows > 0 && cols > 0, "ivv_softmax_rows: bad arguments");
-  softmax_rows_kernel<<<(unsigned)rows, 256, 0, stream>>>(reinterpret_cast<const __half*>(x),
-                                                          reinterpret_cast<__half*>(y), rows, (int)cols, scale);
+  if (x_is_f32)
+    softmax_rows_kernel<float><<<(unsigned)rows, 256, 0, stream>>>(reinterpret_cast<const float*>(x),
+                                                                   reinterpret_cast<__half*>(y), rows, (int)cols, scale);
+  else
+    softmax_rows_kernel<__half><<<(unsigned)rows, 256, 0, stream>>>(reinterpret_cast<const __half*>(x),
+                                                                    reinterpret_cast<__half*>(y), rows, (int)cols, scale);
   IVV_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -30,7 +30,7 @@ SIGNATURES = {
     "ivv_abi_version": (c_i32, []),
     "ivv_last_error": (ctypes.c_char_p, []),
     "ivv_gemm": (c_i32, [ctypes.POINTER(GemmArgs), c_void_p]),
-    "ivv_im2col_s2": (c_i32, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_void_p]),
+    "ivv_im2col_s2": (c_i32, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i32, c_void_p]),
     "ivv_groupnorm": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i32, c_i64, c_f32, c_i32,
                               c_void_p, c_size, c_void_p]),
     "ivv_groupnorm_ws_bytes": (c_size, [c_i64, c_i32, c_i64]),
@@ -39,7 +39,7 @@ SIGNATURES = {
     "ivv_attention": (c_i32, [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64,
                               c_i32, c_i32, c_f32, c_void_p]),
     "ivv_temporal_attention": (c_i32, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i32, c_f32, c_void_p]),
-    "ivv_softmax_rows": (c_i32, [c_void_p, c_void_p, c_i64, c_i64, c_f32, c_void_p]),
+    "ivv_softmax_rows": (c_i32, [c_void_p, c_i32, c_void_p, c_i64, c_i64, c_f32, c_void_p]),
     "ivv_upsample_nearest": (c_i32, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_void_p]),
     "ivv_concat_channels": (c_i32, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_void_p]),
     "ivv_ncfhw_to_frames": (c_i32, [c_void_p, c_i32, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_void_p]),

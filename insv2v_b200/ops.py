@@ -122,13 +122,14 @@ def conv3x3(x, wgt, n_img, h, w, bias=None, rowbias=None, rowbias_group=0, resid
                 rowbias_group=rowbias_group, residual=residual, out=out, out_f32=out_f32)
 
 
-def conv3x3_s2(x, wgt_im2col, n_img, h, w, bias=None):
-    """stride-2 3x3 conv, pad 1 (Downsample3D, resnet.py:99-107): im2col gather then one tcgen05 GEMM."""
+def conv3x3_s2(x, wgt_im2col, n_img, h, w, bias=None, pad=1):
+    """stride-2 3x3 conv: im2col gather then one tcgen05 GEMM. pad=1: Downsample3D (resnet.py:99-107);
+    pad=0: VAE encoder Downsample (zero pad right/bottom only, vqvae/model.py:67-71)."""
     _chk16(x, "x")
     c = x.shape[-1]
-    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    ho, wo = (h - 2 + pad) // 2 + 1, (w - 2 + pad) // 2 + 1
     cols = empty((n_img * ho * wo, 9 * c), F16, x.device)
-    _lib.check(_lib.load().ivv_im2col_s2(_p(x), _p(cols), n_img, h, w, c, ho, wo, _s()), "ivv_im2col_s2")
+    _lib.check(_lib.load().ivv_im2col_s2(_p(x), _p(cols), n_img, h, w, c, ho, wo, pad, _s()), "ivv_im2col_s2")
     _count()
     return gemm(cols, wgt_im2col, n_img=1, h=1, w=n_img * ho * wo, c=9 * c, bias=bias), ho, wo
 
@@ -207,11 +208,13 @@ def temporal_attention(qkv, clips, frames, hw, c, heads, scale=None, out=None):
 
 
 def softmax_rows(x, scale, out=None):
-    _chk16(x, "x")
+    if not x.is_cuda or x.dtype not in (F16, torch.float32) or not x.is_contiguous():
+        raise ValueError("softmax_rows: expected contiguous CUDA fp16/fp32")
     rows, cols = x.shape
     if out is None:
         out = empty(x.shape, F16, x.device)
-    _lib.check(_lib.load().ivv_softmax_rows(_p(x), _p(out), rows, cols, float(scale), _s()), "ivv_softmax_rows")
+    _lib.check(_lib.load().ivv_softmax_rows(_p(x), int(x.dtype == torch.float32), _p(out), rows, cols, float(scale),
+                                            _s()), "ivv_softmax_rows")
     _count()
     return out
 

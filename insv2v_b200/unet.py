@@ -1,0 +1,713 @@
+"""Drop-in for the reference's `modules.video_unet_temporal.unet.UNet3DConditionModel` (unet.py:37-434).
+
+Same constructor arguments (diffusers-style config, `configs/instruct_v2v_inference.yaml:23-68`), same
+`forward(sample, timestep, encoder_hidden_states, class_labels, attention_mask, return_dict, video_start_index)`
+contract, same state-dict key names and shapes (checked against tests/golden/schema_unet_*.json),
+so `pl_trainer/inference/inference.py` and `insv2v_run_loveu_tgve.py` run on it unchanged. The nn.Module tree below only
+HOLDS parameters under the reference's names; the arithmetic is the plan in `_Engine`, a straight-line sequence of
+C-ABI calls into libivv_b200.so (hand-written sm_100a kernels) over channels-last fp16 frames, optionally replayed as a
+CUDA graph. There is no PyTorch/CPU fallback: without the CUDA library `forward` raises.
+"""
+import math
+from dataclasses import dataclass
+from typing import Optional, Tuple, Union
+
+import torch
+from torch import nn
+
+from . import ops
+
+F16 = torch.float16
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# parameter-holding skeleton (names mirror the reference; nothing here is ever called)
+# ------------------------------------------------------------------------------------------------------------------
+class _Holder(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter holder: the arithmetic runs in insv2v_b200.unet._Engine")
+
+
+class _Attn(_Holder):
+    """diffusers Attention parameters: to_q/to_k/to_v without bias, to_out.0 with bias."""
+
+    def __init__(self, query_dim, kv_dim, inner_dim):
+        super().__init__()
+        self.to_q = nn.Linear(query_dim, inner_dim, bias=False)
+        self.to_k = nn.Linear(kv_dim, inner_dim, bias=False)
+        self.to_v = nn.Linear(kv_dim, inner_dim, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(inner_dim, query_dim), nn.Dropout(0.0)])
+
+
+class _GEGLU(_Holder):
+    def __init__(self, dim, inner):
+        super().__init__()
+        self.proj = nn.Linear(dim, inner * 2)
+
+
+class _FeedForward(_Holder):
+    def __init__(self, dim):
+        super().__init__()
+        self.net = nn.ModuleList([_GEGLU(dim, dim * 4), nn.Dropout(0.0), nn.Linear(dim * 4, dim)])
+
+
+class _Resnet(_Holder):
+    """ResnetBlock3D parameters (resnet.py:110-172)."""
+
+    def __init__(self, cin, cout, temb, groups, eps):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(groups, cin, eps=eps)
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb, cout)
+        self.norm2 = nn.GroupNorm(groups, cout, eps=eps)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        if cin != cout:
+            self.conv_shortcut = nn.Conv2d(cin, cout, 1)
+        self.cin, self.cout = cin, cout
+
+
+class _BasicBlock(_Holder):
+    def __init__(self, dim, ctx_dim):
+        super().__init__()
+        self.attn1 = _Attn(dim, dim, dim)
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn2 = _Attn(dim, ctx_dim, dim)
+        self.norm2 = nn.LayerNorm(dim)
+        self.ff = _FeedForward(dim)
+        self.norm3 = nn.LayerNorm(dim)
+
+
+class _SpatialTransformer(_Holder):
+    """Transformer3DModel parameters (attention.py:33-89), use_linear_projection=False."""
+
+    def __init__(self, dim, heads, ctx_dim, groups):
+        super().__init__()
+        self.norm = nn.GroupNorm(groups, dim, eps=1e-6)
+        self.proj_in = nn.Conv2d(dim, dim, 1)
+        self.transformer_blocks = nn.ModuleList([_BasicBlock(dim, ctx_dim)])
+        self.proj_out = nn.Conv2d(dim, dim, 1)
+        self.heads = heads
+
+
+class _PosEnc(_Holder):
+    def __init__(self, dim, max_len):
+        super().__init__()
+        position = torch.arange(max_len).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, dim, 2) * (-math.log(10000.0) / dim))
+        pe = torch.zeros(1, max_len, dim)
+        pe[0, :, 0::2] = torch.sin(position * div_term)
+        pe[0, :, 1::2] = torch.cos(position * div_term)
+        self.register_buffer("pe", pe)
+
+
+class _TemporalAttn(_Attn):
+    def __init__(self, dim, max_len, use_pe):
+        super().__init__(dim, dim, dim)
+        self.pos_encoder = _PosEnc(dim, max_len) if use_pe else None
+
+
+class _TemporalBlock(_Holder):
+    def __init__(self, dim, n_attn, max_len, use_pe):
+        super().__init__()
+        self.attention_blocks = nn.ModuleList([_TemporalAttn(dim, max_len, use_pe) for _ in range(n_attn)])
+        self.norms = nn.ModuleList([nn.LayerNorm(dim) for _ in range(n_attn)])
+        self.ff = _FeedForward(dim)
+        self.ff_norm = nn.LayerNorm(dim)
+
+
+class _TemporalTransformer(_Holder):
+    def __init__(self, dim, heads, n_layers, n_attn, max_len, use_pe):
+        super().__init__()
+        self.norm = nn.GroupNorm(32, dim, eps=1e-6)
+        self.proj_in = nn.Linear(dim, dim)
+        self.transformer_blocks = nn.ModuleList([_TemporalBlock(dim, n_attn, max_len, use_pe)
+                                                 for _ in range(n_layers)])
+        self.proj_out = nn.Linear(dim, dim)
+        self.heads = heads
+
+
+class _MotionModule(_Holder):
+    """VanillaTemporalModule parameters (motion_module.py:42-69); proj_out zero-initialised as in the reference."""
+
+    def __init__(self, dim, kw):
+        super().__init__()
+        types = tuple(kw.get("attention_block_types", ("Temporal_Self", "Temporal_Self")))
+        if any(t != "Temporal_Self" for t in types):
+            raise NotImplementedError(f"attention_block_types {types}: only Temporal_Self is used by InsV2V")
+        if kw.get("temporal_attention_dim_div", 1) != 1:
+            raise NotImplementedError("temporal_attention_dim_div != 1")
+        self.temporal_transformer = _TemporalTransformer(
+            dim, kw.get("num_attention_heads", 8), kw.get("num_transformer_block", 2), len(types),
+            kw.get("temporal_position_encoding_max_len", 24), kw.get("temporal_position_encoding", True))
+        if kw.get("zero_initialize", True):
+            nn.init.zeros_(self.temporal_transformer.proj_out.weight)
+            nn.init.zeros_(self.temporal_transformer.proj_out.bias)
+
+
+class _Resample(_Holder):
+    def __init__(self, ch, stride):
+        super().__init__()
+        self.conv = nn.Conv2d(ch, ch, 3, stride=stride, padding=1)
+
+
+class _Block(_Holder):
+    def __init__(self):
+        super().__init__()
+        self.gradient_checkpointing = False
+
+
+class _TimestepEmbedding(_Holder):
+    def __init__(self, cin, dim):
+        super().__init__()
+        self.linear_1 = nn.Linear(cin, dim)
+        self.linear_2 = nn.Linear(dim, dim)
+
+
+class _Config(dict):
+    """diffusers FrozenDict stand-in: `unet.config.in_channels` and `unet.config['in_channels']` both work."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError as e:
+            raise AttributeError(k) from e
+
+
+@dataclass
+class UNet3DConditionOutput:
+    sample: torch.Tensor
+
+    def __getitem__(self, i):
+        return (self.sample,)[i]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the model
+# ------------------------------------------------------------------------------------------------------------------
+class UNet3DConditionModel(nn.Module):
+    _supports_gradient_checkpointing = True
+
+    def __init__(
+        self,
+        sample_size: Optional[int] = None,
+        in_channels: int = 4,
+        out_channels: int = 4,
+        center_input_sample: bool = False,
+        flip_sin_to_cos: bool = True,
+        freq_shift: int = 0,
+        down_block_types: Tuple[str] = ("CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "CrossAttnDownBlock3D",
+                                        "DownBlock3D"),
+        mid_block_type: str = "UNetMidBlock3DCrossAttn",
+        up_block_types: Tuple[str] = ("UpBlock3D", "CrossAttnUpBlock3D", "CrossAttnUpBlock3D", "CrossAttnUpBlock3D"),
+        only_cross_attention: Union[bool, Tuple[bool]] = False,
+        block_out_channels: Tuple[int] = (320, 640, 1280, 1280),
+        layers_per_block: int = 2,
+        downsample_padding: int = 1,
+        mid_block_scale_factor: float = 1,
+        act_fn: str = "silu",
+        norm_num_groups: int = 32,
+        norm_eps: float = 1e-5,
+        cross_attention_dim: int = 1280,
+        attention_head_dim: Union[int, Tuple[int]] = 8,
+        dual_cross_attention: bool = False,
+        use_linear_projection: bool = False,
+        class_embed_type: Optional[str] = None,
+        num_class_embeds: Optional[int] = None,
+        upcast_attention: bool = False,
+        resnet_time_scale_shift: str = "default",
+        use_motion_module=True,
+        motion_module_resolutions=(1, 2, 4, 8),
+        motion_module_mid_block=True,
+        motion_module_decoder_only=False,
+        motion_module_type="Vanilla",
+        motion_module_kwargs={},
+    ):
+        super().__init__()
+        cfg = {k: v for k, v in locals().items() if k not in ("self", "__class__", "cfg")}
+        cfg["norm_eps"] = norm_eps = float(norm_eps)  # plain YAML loaders hand over the string '1e-05' 
+        self._internal_dict = _Config(cfg)
+        # options the InsV2V configs never enable are rejected loudly rather than silently mis-computed
+        if mid_block_type != "UNetMidBlock3DCrossAttn":
+            raise ValueError(f"unknown mid_block_type : {mid_block_type}")
+        for flag, name in ((dual_cross_attention, "dual_cross_attention"), (use_linear_projection,
+                           "use_linear_projection"), (upcast_attention, "upcast_attention")):
+            if flag:
+                raise NotImplementedError(f"{name}=True is not used by InsV2V and not implemented")
+        if class_embed_type is not None or num_class_embeds is not None:
+            raise NotImplementedError("class embeddings are not used by InsV2V")
+        if resnet_time_scale_shift != "default" or act_fn not in ("silu", "swish"):
+            raise NotImplementedError("only resnet_time_scale_shift='default' and act_fn='silu' are implemented")
+        if only_cross_attention not in (False, (False,) * len(down_block_types), [False] * len(down_block_types)):
+            raise NotImplementedError("only_cross_attention")
+        if use_motion_module and motion_module_type != "Vanilla":
+            raise ValueError(motion_module_type)
+
+        self.sample_size = sample_size
+        boc = tuple(block_out_channels)
+        nlev = len(boc)
+        heads = (attention_head_dim,) * nlev if isinstance(attention_head_dim, int) else tuple(attention_head_dim)
+        temb_dim = boc[0] * 4
+        g, eps = norm_num_groups, norm_eps
+        mmk = dict(motion_module_kwargs)
+
+        def motion(ch, res, down):
+            ok = use_motion_module and (res in motion_module_resolutions) and not (down and motion_module_decoder_only)
+            return _MotionModule(ch, mmk) if ok else None
+
+        self.conv_in = nn.Conv2d(in_channels, boc[0], 3, padding=1)
+        self.time_embedding = _TimestepEmbedding(boc[0], temb_dim)
+
+        self.down_blocks = nn.ModuleList()
+        out_ch = boc[0]
+        for i, btype in enumerate(down_block_types):
+            in_ch, out_ch = out_ch, boc[i]
+            blk = _Block()
+            blk.has_cross_attention = btype == "CrossAttnDownBlock3D"
+            if btype not in ("CrossAttnDownBlock3D", "DownBlock3D"):
+                raise ValueError(f"{btype} does not exist.")
+            blk.resnets = nn.ModuleList([_Resnet(in_ch if j == 0 else out_ch, out_ch, temb_dim, g, eps)
+                                         for j in range(layers_per_block)])
+            if blk.has_cross_attention:
+                blk.attentions = nn.ModuleList([_SpatialTransformer(out_ch, heads[i], cross_attention_dim, g)
+                                                for _ in range(layers_per_block)])
+            mms = [motion(out_ch, 2 ** i, True) for _ in range(layers_per_block)]
+            blk.motion_modules = nn.ModuleList([m for m in mms if m is not None])
+            blk.has_motion = mms[0] is not None
+            blk.downsamplers = nn.ModuleList([_Resample(out_ch, 2)]) if i != nlev - 1 else None
+            self.down_blocks.append(blk)
+
+        mid = _Block()
+        mid.has_cross_attention = True
+        mid.resnets = nn.ModuleList([_Resnet(boc[-1], boc[-1], temb_dim, g, eps) for _ in range(2)])
+        mid.attentions = nn.ModuleList([_SpatialTransformer(boc[-1], heads[-1], cross_attention_dim, g)])
+        mid_mm = _MotionModule(boc[-1], mmk) if (use_motion_module and motion_module_mid_block) else None
+        mid.motion_modules = nn.ModuleList([mid_mm] if mid_mm is not None else [])
+        mid.has_motion = mid_mm is not None
+        self.mid_block = mid
+
+        self.num_upsamplers = 0
+        self.up_blocks = nn.ModuleList()
+        rboc, rheads = tuple(reversed(boc)), tuple(reversed(heads))
+        out_ch = rboc[0]
+        for i, btype in enumerate(up_block_types):
+            prev_ch, out_ch = out_ch, rboc[i]
+            in_ch = rboc[min(i + 1, nlev - 1)]
+            blk = _Block()
+            blk.has_cross_attention = btype == "CrossAttnUpBlock3D"
+            if btype not in ("CrossAttnUpBlock3D", "UpBlock3D"):
+                raise ValueError(f"{btype} does not exist.")
+            n = layers_per_block + 1
+            rs = []
+            for j in range(n):
+                skip_ch = in_ch if j == n - 1 else out_ch
+                rin = prev_ch if j == 0 else out_ch
+                rs.append(_Resnet(rin + skip_ch, out_ch, temb_dim, g, eps))
+            blk.resnets = nn.ModuleList(rs)
+            if blk.has_cross_attention:
+                blk.attentions = nn.ModuleList([_SpatialTransformer(out_ch, rheads[i], cross_attention_dim, g)
+                                                for _ in range(n)])
+            mms = [motion(out_ch, 2 ** (nlev - 1 - i), False) for _ in range(n)]
+            blk.motion_modules = nn.ModuleList([m for m in mms if m is not None])
+            blk.has_motion = mms[0] is not None
+            if i != nlev - 1:
+                blk.upsamplers = nn.ModuleList([_Resample(out_ch, 1)])
+                self.num_upsamplers += 1
+            else:
+                blk.upsamplers = None
+            self.up_blocks.append(blk)
+
+        self.conv_norm_out = nn.GroupNorm(g, boc[0], eps=eps)
+        self.conv_out = nn.Conv2d(boc[0], out_channels, 3, padding=1)
+
+        self._engine = None
+        self.use_cuda_graph = True
+
+    # ---- reference API surface -------------------------------------------------------------------------------
+    @property
+    def config(self):
+        return self._internal_dict
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def enable_xformers_memory_efficient_attention(self, attention_op=None):
+        """No-op: attention always runs in the fused tcgen05 kernel (reference: instruct_p2p_video.py:27)."""
+
+    def disable_xformers_memory_efficient_attention(self):
+        pass
+
+    def enable_gradient_checkpointing(self):
+        """Inference-only implementation; kept so that the reference container can call it (:28)."""
+        for m in self.modules():
+            if isinstance(m, _Block):
+                m.gradient_checkpointing = True
+
+    def _set_gradient_checkpointing(self, module, value=False):
+        if isinstance(module, _Block):
+            module.gradient_checkpointing = value
+
+    def set_attention_slice(self, slice_size):
+        """Accepted for API compatibility (unet.py:227-290); the fused kernel never materialises score matrices."""
+
+    def _apply(self, fn, recurse=True):
+        self._engine = None  # packed weights follow the parameters (device / dtype moves)
+        return super()._apply(fn, recurse)
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        self._engine = None
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def invalidate(self):
+        """Drop packed weights and captured graphs (call after mutating parameters in place)."""
+        self._engine = None
+
+    # ---- forward ---------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, attention_mask=None,
+                return_dict: bool = True, video_start_index: int = 0):
+        if sample.dim() != 5:
+            raise ValueError(f"Expected sample to have ndim=5 (b c f h w), got {sample.dim()}")
+        if not sample.is_cuda:
+            raise RuntimeError("insv2v_b200.UNet3DConditionModel runs only on CUDA (sm_100a); there is no CPU path. "
+                               "Use oracle/insv2v_oracle.py for a CPU evaluation.")
+        if self._engine is None or self._engine.device != sample.device:
+            self._engine = _Engine(self, sample.device)
+        # timestep handling mirrors unet.py:343-356
+        t = timestep
+        if not torch.is_tensor(t):
+            t = torch.tensor([t], dtype=torch.float32, device=sample.device)
+        elif t.dim() == 0:
+            t = t[None]
+        t = t.to(device=sample.device, dtype=torch.float32).expand(sample.shape[0]).contiguous()
+        # attention_mask is converted by the reference (unet.py:334-336) but never reaches the transformers
+        # (unet_blocks.py:353 does not forward it): it has no effect there either.
+        out = self._engine.run(sample, t, encoder_hidden_states, int(video_start_index), self.use_cuda_graph)
+        out = out.to(sample.dtype) if sample.dtype != out.dtype else out
+        if not return_dict:
+            return (out,)
+        return UNet3DConditionOutput(sample=out)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# execution plan
+# ------------------------------------------------------------------------------------------------------------------
+def _h(t, device):
+    return t.detach().to(device=device, dtype=F16).contiguous()
+
+
+class _Engine:
+    """Packed fp16 weights + the launch sequence of one UNet forward over channels-last frames [b*f*h*w, c]."""
+
+    def __init__(self, model: UNet3DConditionModel, device):
+        self.device = device
+        self.cfg = model.config
+        self.graphs = {}
+        m = model
+        dev = device
+        self.w = {}
+        W = self.w
+
+        def pk_resnet(name, r):
+            W[name] = dict(
+                n1=(_h(r.norm1.weight, dev), _h(r.norm1.bias, dev)), eps=r.norm1.eps, groups=r.norm1.num_groups,
+                c1=(ops.pack_conv3x3(r.conv1.weight.detach().to(dev)), _h(r.conv1.bias, dev)),
+                n2=(_h(r.norm2.weight, dev), _h(r.norm2.bias, dev)),
+                c2=(ops.pack_conv3x3(r.conv2.weight.detach().to(dev)), _h(r.conv2.bias, dev)),
+                sc=(ops.pack_linear(r.conv_shortcut.weight.detach().to(dev)), _h(r.conv_shortcut.bias, dev))
+                if hasattr(r, "conv_shortcut") else None,
+                cout=r.cout)
+            self._temb_layers.append((name, r.time_emb_proj))
+
+        def pk_attn(a, fuse_qkv):
+            d = dict(out=(ops.pack_linear(a.to_out[0].weight.detach().to(dev)), _h(a.to_out[0].bias, dev)))
+            if fuse_qkv:
+                d["qkv"] = ops.pack_linear(torch.cat([a.to_q.weight, a.to_k.weight, a.to_v.weight], 0).detach().to(dev))
+            else:
+                d["q"] = ops.pack_linear(a.to_q.weight.detach().to(dev))
+                d["kv"] = ops.pack_linear(torch.cat([a.to_k.weight, a.to_v.weight], 0).detach().to(dev))
+            return d
+
+        def pk_ff(ff):
+            gw, gb = ops.pack_geglu(ff.net[0].proj.weight.detach().to(dev), ff.net[0].proj.bias.detach().to(dev))
+            return dict(geglu=(gw, gb), out=(ops.pack_linear(ff.net[2].weight.detach().to(dev)),
+                                             _h(ff.net[2].bias, dev)))
+
+        def pk_ln(ln):
+            return (_h(ln.weight, dev), _h(ln.bias, dev), ln.eps)
+
+        def pk_spatial(name, s):
+            b = s.transformer_blocks[0]
+            W[name] = dict(norm=(_h(s.norm.weight, dev), _h(s.norm.bias, dev)), groups=s.norm.num_groups,
+                           eps=s.norm.eps, heads=s.heads,
+                           pin=(ops.pack_linear(s.proj_in.weight.detach().to(dev)), _h(s.proj_in.bias, dev)),
+                           pout=(ops.pack_linear(s.proj_out.weight.detach().to(dev)), _h(s.proj_out.bias, dev)),
+                           ln1=pk_ln(b.norm1), ln2=pk_ln(b.norm2), ln3=pk_ln(b.norm3),
+                           attn1=pk_attn(b.attn1, True), attn2=pk_attn(b.attn2, False), ff=pk_ff(b.ff))
+
+        def pk_motion(name, mm):
+            t = mm.temporal_transformer
+            blocks = []
+            for tb in t.transformer_blocks:
+                attn = []
+                for a, ln in zip(tb.attention_blocks, tb.norms):
+                    d = pk_attn(a, True)
+                    d["ln"] = pk_ln(ln)
+                    d["pe"] = (a.pos_encoder.pe.detach()[0].to(device=dev, dtype=torch.float32).contiguous()
+                               if a.pos_encoder is not None else None)
+                    attn.append(d)
+                blocks.append(dict(attn=attn, ff_ln=pk_ln(tb.ff_norm), ff=pk_ff(tb.ff)))
+            W[name] = dict(norm=(_h(t.norm.weight, dev), _h(t.norm.bias, dev)), eps=t.norm.eps, heads=t.heads,
+                           pin=(ops.pack_linear(t.proj_in.weight.detach().to(dev)), _h(t.proj_in.bias, dev)),
+                           pout=(ops.pack_linear(t.proj_out.weight.detach().to(dev)), _h(t.proj_out.bias, dev)),
+                           blocks=blocks)
+
+        self._temb_layers = []
+        in_ch = m.conv_in.weight.shape[1]
+        self.cin_pad = (in_ch + 7) // 8 * 8
+        W["conv_in"] = (ops.pack_conv3x3(m.conv_in.weight.detach().to(dev)), _h(m.conv_in.bias, dev))
+        W["te1"] = (ops.pack_linear(m.time_embedding.linear_1.weight.detach().to(dev)),
+                    _h(m.time_embedding.linear_1.bias, dev))
+        W["te2"] = (ops.pack_linear(m.time_embedding.linear_2.weight.detach().to(dev)),
+                    _h(m.time_embedding.linear_2.bias, dev))
+        self.plan = []  # (kind, name, extra)
+        for i, blk in enumerate(m.down_blocks):
+            for j, r in enumerate(blk.resnets):
+                pk_resnet(f"d{i}r{j}", r)
+                self.plan.append(("resnet", f"d{i}r{j}"))
+                if blk.has_cross_attention:
+                    pk_spatial(f"d{i}a{j}", blk.attentions[j])
+                    self.plan.append(("spatial", f"d{i}a{j}"))
+                if blk.has_motion:
+                    pk_motion(f"d{i}m{j}", blk.motion_modules[j])
+                    self.plan.append(("motion", f"d{i}m{j}"))
+                self.plan.append(("push",))
+            if blk.downsamplers is not None:
+                c = blk.downsamplers[0].conv
+                W[f"d{i}down"] = (ops.pack_conv3x3_im2col(c.weight.detach().to(dev)), _h(c.bias, dev))
+                self.plan.append(("down", f"d{i}down"))
+                self.plan.append(("push",))
+        pk_resnet("mr0", m.mid_block.resnets[0])
+        pk_spatial("ma0", m.mid_block.attentions[0])
+        pk_resnet("mr1", m.mid_block.resnets[1])
+        self.plan += [("resnet", "mr0"), ("spatial", "ma0")]
+        if m.mid_block.has_motion:
+            pk_motion("mm0", m.mid_block.motion_modules[0])
+            self.plan.append(("motion", "mm0"))
+        self.plan.append(("resnet", "mr1"))
+        for i, blk in enumerate(m.up_blocks):
+            for j, r in enumerate(blk.resnets):
+                self.plan.append(("pop_cat",))
+                pk_resnet(f"u{i}r{j}", r)
+                self.plan.append(("resnet", f"u{i}r{j}"))
+                if blk.has_cross_attention:
+                    pk_spatial(f"u{i}a{j}", blk.attentions[j])
+                    self.plan.append(("spatial", f"u{i}a{j}"))
+                if blk.has_motion:
+                    pk_motion(f"u{i}m{j}", blk.motion_modules[j])
+                    self.plan.append(("motion", f"u{i}m{j}"))
+            if blk.upsamplers is not None:
+                c = blk.upsamplers[0].conv
+                W[f"u{i}up"] = (ops.pack_conv3x3(c.weight.detach().to(dev)), _h(c.bias, dev))
+                self.plan.append(("up", f"u{i}up"))
+        W["norm_out"] = (_h(m.conv_norm_out.weight, dev), _h(m.conv_norm_out.bias, dev), m.conv_norm_out.eps,
+                         m.conv_norm_out.num_groups)
+        W["conv_out"] = (ops.pack_conv3x3(m.conv_out.weight.detach().to(dev)), _h(m.conv_out.bias, dev))
+        self.out_channels = m.conv_out.weight.shape[0]
+        # all 22 time_emb_proj layers as ONE GEMM: [sum(cout), temb_dim]
+        self.temb_w = ops.pack_linear(torch.cat([l.weight for _, l in self._temb_layers], 0).detach().to(dev))
+        self.temb_b = _h(torch.cat([l.bias for _, l in self._temb_layers], 0), dev)
+        off = 0
+        self.temb_off = {}
+        for name, l in self._temb_layers:
+            self.temb_off[name] = off
+            off += l.weight.shape[0]
+        self.temb_total = off
+        self.num_upsamplers = m.num_upsamplers
+        self.pe_len = None
+        for v in W.values():
+            if isinstance(v, dict) and "blocks" in v:
+                pe = v["blocks"][0]["attn"][0]["pe"]
+                if pe is not None:
+                    self.pe_len = pe.shape[0]
+                break
+
+    # ---- building blocks (x is frames [n*h*w, c] fp16) -------------------------------------------------------
+    def _resnet(self, x, name, st):
+        p = self.w[name]
+        n, h, w, f = st["n"], st["h"], st["w"], st["f"]
+        hcur = ops.groupnorm(x, *p["n1"], n, h * w, p["groups"], f, p["eps"], True)
+        temb = st["temb"][:, self.temb_off[name]:]  # view: row stride temb_total, used through rowbias_ld
+        hcur = ops.gemm(hcur, p["c1"][0], n_img=n, h=h, w=w, c=hcur.shape[-1], taps=9, bias=p["c1"][1],
+                        rowbias=_View(temb, self.temb_total), rowbias_group=f * h * w)
+        hcur = ops.groupnorm(hcur, *p["n2"], n, h * w, p["groups"], f, p["eps"], True)
+        res = x if p["sc"] is None else ops.linear(x, p["sc"][0], bias=p["sc"][1])
+        return ops.conv3x3(hcur, p["c2"][0], n, h, w, bias=p["c2"][1], residual=res)
+
+    def _spatial(self, x, name, st):
+        p = self.w[name]
+        n, h, w, f = st["n"], st["h"], st["w"], st["f"]
+        c = x.shape[-1]
+        s = h * w
+        heads = p["heads"]
+        d = c // heads
+        hs = ops.groupnorm(x, *p["norm"], n, s, p["groups"], 1, p["eps"], False)
+        hs = ops.linear(hs, p["pin"][0], bias=p["pin"][1])
+        # self-attention
+        nrm = ops.layernorm(hs, *p["ln1"][:2], eps=p["ln1"][2])
+        qkv = ops.linear(nrm, p["attn1"]["qkv"])
+        ao = ops.attention(_Col(qkv, 0), _Col(qkv, c), _Col(qkv, 2 * c), n_batch=n, s_q=s, s_kv=s, heads=heads, d=d,
+                           q_ld=3 * c, kv_ld=3 * c)
+        hs = ops.linear(ao, p["attn1"]["out"][0], bias=p["attn1"]["out"][1], residual=hs)
+        # cross-attention: K/V once per clip (the reference repeats ctx per frame, attention.py:96)
+        nrm = ops.layernorm(hs, *p["ln2"][:2], eps=p["ln2"][2])
+        q = ops.linear(nrm, p["attn2"]["q"])
+        kv = ops.linear(st["ctx"], p["attn2"]["kv"])
+        ao = ops.attention(q, _Col(kv, 0), _Col(kv, c), n_batch=n, s_q=s, s_kv=st["ctx_len"], heads=heads, d=d,
+                           q_ld=c, kv_ld=2 * c, kv_div=f)
+        hs = ops.linear(ao, p["attn2"]["out"][0], bias=p["attn2"]["out"][1], residual=hs)
+        # feed-forward (GEGLU fused in the first GEMM's epilogue)
+        nrm = ops.layernorm(hs, *p["ln3"][:2], eps=p["ln3"][2])
+        g = ops.linear(nrm, p["ff"]["geglu"][0], bias=p["ff"]["geglu"][1], geglu=True)
+        hs = ops.linear(g, p["ff"]["out"][0], bias=p["ff"]["out"][1], residual=hs)
+        return ops.linear(hs, p["pout"][0], bias=p["pout"][1], residual=x)
+
+    def _motion(self, x, name, st):
+        p = self.w[name]
+        n, h, w, f, b = st["n"], st["h"], st["w"], st["f"], st["b"]
+        c = x.shape[-1]
+        s = h * w
+        hs = ops.groupnorm(x, *p["norm"], n, s, 32, 1, p["eps"], False)
+        hs = ops.linear(hs, p["pin"][0], bias=p["pin"][1])
+        for blk in p["blocks"]:
+            for a in blk["attn"]:
+                pe = a["pe"]
+                nrm = ops.layernorm(hs, *a["ln"][:2], eps=a["ln"][2], pe=pe, rows_per_frame=s, frames=f,
+                                    pe_start=st["pe_start"])
+                qkv = ops.linear(nrm, a["qkv"])
+                ao = ops.temporal_attention(qkv, b, f, s, c, p["heads"])
+                hs = ops.linear(ao, a["out"][0], bias=a["out"][1], residual=hs)
+            nrm = ops.layernorm(hs, *blk["ff_ln"][:2], eps=blk["ff_ln"][2])
+            g = ops.linear(nrm, blk["ff"]["geglu"][0], bias=blk["ff"]["geglu"][1], geglu=True)
+            hs = ops.linear(g, blk["ff"]["out"][0], bias=blk["ff"]["out"][1], residual=hs)
+        return ops.linear(hs, p["pout"][0], bias=p["pout"][1], residual=x)
+
+    # ---- one forward ---------------------------------------------------------------------------------------
+    def _forward_frames(self, sample, t, ctx, pe_start):
+        b, cin, f, h, w = sample.shape
+        st = dict(b=b, f=f, n=b * f, h=h, w=w, pe_start=pe_start)
+        st["ctx"] = ctx.reshape(-1, ctx.shape[-1]).to(F16).contiguous()
+        st["ctx_len"] = ctx.shape[1]
+        W = self.w
+        # time embedding: sinusoid -> linear_1 -> SiLU -> linear_2 -> SiLU -> all time_emb_proj at once
+        te = ops.timestep_embedding(t, W["te1"][0].shape[2], self.cfg["flip_sin_to_cos"], self.cfg["freq_shift"])
+        te = ops.linear(ops.silu(ops.linear(te, W["te1"][0], bias=W["te1"][1])), W["te2"][0], bias=W["te2"][1])
+        st["temb"] = ops.linear(ops.silu(te), self.temb_w, bias=self.temb_b)  # [b, sum(cout)]
+        x = ops.ncfhw_to_frames(sample, self.cin_pad)
+        x = ops.conv3x3(x, W["conv_in"][0], st["n"], h, w, bias=W["conv_in"][1])
+        skips = [(x, h, w)]
+        default_up = 2 ** self.num_upsamplers
+        forward_size = (h % default_up != 0) or (w % default_up != 0)
+        for step in self.plan:
+            kind = step[0]
+            if kind == "resnet":
+                x = self._resnet(x, step[1], st)
+            elif kind == "spatial":
+                x = self._spatial(x, step[1], st)
+            elif kind == "motion":
+                x = self._motion(x, step[1], st)
+            elif kind == "push":
+                skips.append((x, st["h"], st["w"]))
+            elif kind == "down":
+                wd, bd = W[step[1]]
+                x, st["h"], st["w"] = ops.conv3x3_s2(x, wd, st["n"], st["h"], st["w"], bias=bd)
+            elif kind == "pop_cat":
+                sk, sh, sw = skips.pop()
+                assert (sh, sw) == (st["h"], st["w"]), "skip/feature size mismatch"
+                x = ops.concat_channels(x, sk)
+            elif kind == "up":
+                wu, bu = W[step[1]]
+                if forward_size:
+                    ho, wo = skips[-1][1], skips[-1][2]  # unet.py:409-410
+                else:
+                    ho, wo = 2 * st["h"], 2 * st["w"]
+                x, st["h"], st["w"] = ops.upsample_nearest(x, st["n"], st["h"], st["w"], ho, wo)
+                x = ops.conv3x3(x, wu, st["n"], st["h"], st["w"], bias=bu)
+        g, be, eps, groups = W["norm_out"]
+        x = ops.groupnorm(x, g, be, st["n"], st["h"] * st["w"], groups, f, eps, True)
+        x = ops.conv3x3(x, W["conv_out"][0], st["n"], st["h"], st["w"], bias=W["conv_out"][1], out_f32=True)
+        return ops.frames_to_ncfhw(x, b, self.out_channels, f, st["h"], st["w"], torch.float32)
+
+    def run(self, sample, t, ctx, video_start_index, use_graph):
+        f = sample.shape[2]
+        pe_start = video_start_index
+        if self.pe_len is not None:
+            # PositionalEncoding.forward, motion_module.py:236-240
+            if pe_start + f > self.pe_len:
+                pe_start = pe_start - self.pe_len
+            if pe_start < 0:
+                raise ValueError(f"start_index must be non-negative, but got {pe_start}")
+        if ctx.shape[0] != sample.shape[0]:
+            raise ValueError(f"encoder_hidden_states batch {ctx.shape[0]} != sample batch {sample.shape[0]}")
+        if not use_graph:
+            return self._forward_frames(sample, t, ctx, pe_start)
+        key = (tuple(sample.shape), sample.dtype, tuple(ctx.shape), ctx.dtype, pe_start)
+        g = self.graphs.get(key)
+        if g is None:
+            g = _Graph(self, sample, t, ctx, pe_start)
+            self.graphs[key] = g
+        return g.replay(sample, t, ctx)
+
+
+class _Graph:
+    """CUDA-graph capture of one forward: static input buffers, one cudaGraphLaunch per UNet call instead of ~1200
+    kernel launches issued from Python."""
+
+    def __init__(self, eng, sample, t, ctx, pe_start):
+        self.s_in = sample.clone()
+        self.t_in = t.clone()
+        self.c_in = ctx.clone()
+        stream = torch.cuda.Stream(device=sample.device)
+        stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(stream):
+            eng._forward_frames(self.s_in, self.t_in, self.c_in, pe_start)  # warm-up: lazy kernel attribute setup
+        torch.cuda.current_stream().wait_stream(stream)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = eng._forward_frames(self.s_in, self.t_in, self.c_in, pe_start)
+
+    def replay(self, sample, t, ctx):
+        self.s_in.copy_(sample)
+        self.t_in.copy_(t)
+        self.c_in.copy_(ctx)
+        self.graph.replay()
+        return self.out.clone()
+
+
+class _View:
+    """A column window of a row-major fp16 buffer passed by pointer + leading dimension (no copy)."""
+
+    def __init__(self, t, ld):
+        self.t, self.ld = t, ld
+        self.is_cuda, self.dtype = t.is_cuda, t.dtype
+        self.shape = (t.shape[0], ld)
+        self.device = t.device
+
+    def data_ptr(self):
+        return self.t.data_ptr()
+
+    def is_contiguous(self):
+        return True
+
+    def dim(self):
+        return 2
+
+
+def _Col(t, off):
+    """Pointer to column `off` of a contiguous [rows, ld] buffer (attention takes explicit leading dimensions)."""
+    return t[:, off:]

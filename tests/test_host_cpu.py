@@ -1,0 +1,174 @@
+"""CPU suite, part 2: host-side logic of the product — state-dict schema identity with the reference, the C-ABI
+library's exported symbols, weight packing, clip sharding (world_size 2 over gloo)."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from tests.helpers import ROOT, schema
+
+
+def _meta_sd(module):
+    return {k: tuple(v.shape) for k, v in module.state_dict().items()}
+
+
+@pytest.mark.parametrize("tag", ["micro", "tiny", "full"])
+def test_unet_state_dict_schema_is_the_references(tag):
+    from insv2v_b200.unet import UNet3DConditionModel
+    from oracle import insv2v_oracle as O
+    cfg = {"micro": O.UNET_CONFIG_MICRO, "tiny": O.UNET_CONFIG_TINY, "full": O.UNET_CONFIG_FULL}[tag]
+    with torch.device("meta"):
+        m = UNet3DConditionModel(**cfg)
+    assert _meta_sd(m) == schema(f"unet_{tag}")
+    names = [n for n, _ in m.named_parameters()]
+    assert any("motion" in n for n in names)  # instruct_p2p_video.py:239 selects trainable params by this substring
+
+
+def test_unet_accepts_the_yaml_param_dict_and_rejects_unknown_block():
+    from insv2v_b200.unet import UNet3DConditionModel
+    import yaml
+    params = yaml.safe_load("""
+      in_channels: 8
+      out_channels: 4
+      act_fn: silu
+      attention_head_dim: 8
+      block_out_channels: [64, 64, 128, 128]
+      cross_attention_dim: 64
+      down_block_types: [CrossAttnDownBlock3D, CrossAttnDownBlock3D, CrossAttnDownBlock3D, DownBlock3D]
+      up_block_types: [UpBlock3D, CrossAttnUpBlock3D, CrossAttnUpBlock3D, CrossAttnUpBlock3D]
+      downsample_padding: 1
+      layers_per_block: 1
+      mid_block_scale_factor: 1
+      norm_eps: 1e-05
+      norm_num_groups: 32
+      sample_size: 64
+      use_motion_module: true
+      motion_module_resolutions: [1, 2, 4, 8]
+      motion_module_mid_block: false
+      motion_module_decoder_only: false
+      motion_module_type: Vanilla
+      motion_module_kwargs:
+        num_attention_heads: 8
+        num_transformer_block: 1
+        attention_block_types: [Temporal_Self, Temporal_Self]
+        temporal_position_encoding: true
+        temporal_position_encoding_max_len: 32
+        temporal_attention_dim_div: 1
+    """)
+    assert isinstance(params["norm_eps"], str)  # plain PyYAML yields '1e-05' (SURVEY §2.2): must be coerced
+    with torch.device("meta"):
+        m = UNet3DConditionModel(**params)
+    assert m.config.norm_eps == 1e-5 and m.config["sample_size"] == 64
+    assert _meta_sd(m) == schema("unet_micro")
+    # zero-initialised motion proj_out as in the reference (motion_module.py:68-69)
+    m2 = UNet3DConditionModel(**params)
+    po = m2.down_blocks[0].motion_modules[0].temporal_transformer.proj_out
+    assert float(po.weight.detach().abs().max()) == 0.0 and float(po.bias.detach().abs().max()) == 0.0
+    bad = dict(params, down_block_types=["Nope"] * 4)
+    with pytest.raises(ValueError):
+        UNet3DConditionModel(**bad)
+    with pytest.raises(RuntimeError):  # no CPU path
+        m2(torch.zeros(1, 8, 2, 8, 8), 1, torch.zeros(1, 77, 64))
+
+
+@pytest.mark.parametrize("tag", ["tiny", "full"])
+def test_vae_state_dict_schema_is_the_references(tag):
+    from insv2v_b200.vae import AutoencoderKL
+    from oracle import insv2v_oracle as O
+    cfg = {"tiny": O.VAE_CONFIG_TINY, "full": O.VAE_CONFIG_FULL}[tag]
+    with torch.device("meta"):
+        v = AutoencoderKL(**cfg, lossconfig={"target": "torch.nn.Identity"})
+    sd = _meta_sd(v)
+    ref = schema(f"vae_{tag}")  # decoder.* + post_quant_conv.* of the reference
+    assert {k: s for k, s in sd.items() if k.startswith(("decoder.", "post_quant_conv."))} == ref
+    assert "quant_conv.weight" in sd and sd["quant_conv.weight"] == (8, 8, 1, 1)
+    assert "encoder.down.0.downsample.conv.weight" in sd and "encoder.mid.attn_1.q.weight" in sd
+
+
+def test_library_exports_every_declared_symbol():
+    from insv2v_b200 import lib
+    hdr = open(os.path.join(ROOT, "include", "ivv.h")).read()
+    declared = set(re.findall(r"\b(ivv_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(lib.SIGNATURES), declared ^ set(lib.SIGNATURES)
+    if not os.path.exists(lib.LIB_PATH):
+        pytest.skip("libivv_b200.so not built in this checkout (run __graft_entry__.build())")
+    L = lib.load()
+    for name in declared:
+        assert hasattr(L, name)
+    assert L.ivv_abi_version() == 1
+    assert L.ivv_groupnorm_ws_bytes(48, 32, 16) == 3 * 32 * 2 * 8
+
+
+def test_error_path_reports_through_last_error():
+    """Argument validation happens before any CUDA call, so it is testable without a GPU."""
+    import ctypes
+    from insv2v_b200 import lib
+    if not os.path.exists(lib.LIB_PATH):
+        pytest.skip("library not built")
+    L = lib.load()
+    rc = L.ivv_layernorm(None, None, None, None, 10, 320, 1e-5, None, 0, 0, 0, None)
+    assert rc != 0 and b"null" in L.ivv_last_error()
+    args = lib.GemmArgs()
+    args.taps = 5
+    assert L.ivv_gemm(ctypes.byref(args), None) != 0 and b"taps" in L.ivv_last_error()
+    with pytest.raises(RuntimeError):
+        lib.check(1, "x")
+
+
+def test_weight_packing():
+    from insv2v_b200 import ops
+    w = torch.randn(12, 10, 3, 3)
+    p = ops.pack_conv3x3(w)
+    assert p.shape == (9, 12, 16) and p.dtype == torch.float16
+    assert torch.equal(p[4, :, :10], w[:, :, 1, 1].half()) and (p[:, :, 10:] == 0).all()
+    p2 = ops.pack_conv3x3_im2col(torch.randn(6, 8, 3, 3))
+    assert p2.shape == (1, 6, 72)
+    wl = torch.randn(512, 64)
+    b = torch.randn(512)
+    gw, gb = ops.pack_geglu(wl, b)
+    # tile t holds hidden rows [64t, 64t+64) then the matching gate rows
+    assert torch.equal(gw[0, 128:192], wl[64:128].half()) and torch.equal(gw[0, 192:256], wl[256 + 64:256 + 128].half())
+    assert torch.equal(gb[64:128], b[256:320].half())
+    with pytest.raises(ValueError):
+        ops.pack_geglu(torch.randn(100, 8), torch.randn(100))
+
+
+def test_clip_sharding_single_process():
+    from insv2v_b200.parallel import clips_for_rank
+    assert clips_for_rank(8, 0, 8) == [0] and clips_for_rank(8, 3, 4) == [3, 7] and clips_for_rank(3, 3, 4) == []
+    assert sorted(sum((clips_for_rank(11, r, 4) for r in range(4)), [])) == list(range(11))
+    with pytest.raises(ValueError):
+        clips_for_rank(4, 4, 4)
+
+
+_WORKER = r"""
+import os, sys, torch
+sys.path.insert(0, os.environ["IVV_ROOT"])
+import torch.distributed as dist
+from insv2v_b200 import parallel
+rank, world, _ = parallel.init_from_env("gloo")
+n_clips = int(os.environ["IVV_CLIPS"])
+inputs = [torch.full((2, 3, 4, 5), float(i)) for i in range(n_clips)]
+out = parallel.run_clips(lambda x: x * 2 + 1, inputs, rank, world)
+ref = torch.stack([x * 2 + 1 for x in inputs])
+assert out.shape == ref.shape and torch.equal(out, ref), (rank, out[:, 0, 0, 0, 0])
+dist.barrier()
+dist.destroy_process_group()
+sys.stdout.write(f"[rank{rank}-ok]\n"); sys.stdout.flush()
+"""
+
+
+@pytest.mark.parametrize("n_clips", [2, 5])
+def test_clip_parallel_world_size_2_gloo(tmp_path, n_clips):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, IVV_ROOT=ROOT, IVV_CLIPS=str(n_clips))
+    port = 29500 + (os.getpid() % 2000)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), str(script)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "[rank0-ok]" in r.stdout and "[rank1-ok]" in r.stdout
