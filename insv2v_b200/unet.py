@@ -677,15 +677,20 @@ class _Graph:
             eng._forward_frames(self.s_in, self.t_in, self.c_in, pe_start)  # warm-up: lazy kernel attribute setup
         torch.cuda.current_stream().wait_stream(stream)
         torch.cuda.synchronize()
+        from . import lib as _lib
+        n0 = _lib.LAUNCH_COUNT
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = eng._forward_frames(self.s_in, self.t_in, self.c_in, pe_start)
+        self.n_launches = _lib.LAUNCH_COUNT - n0  # kernels inside the graph: counted again on every replay
+        self._lib = _lib
 
     def replay(self, sample, t, ctx):
         self.s_in.copy_(sample)
         self.t_in.copy_(t)
         self.c_in.copy_(ctx)
         self.graph.replay()
+        self._lib.LAUNCH_COUNT += self.n_launches
         return self.out.clone()
 
 
