@@ -35,7 +35,7 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box, bool swizzle128) {
+                  const uint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   IVV_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver (no CUDA driver / GPU?)");
   cuuint64_t gdim[5];
@@ -56,7 +56,7 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
   IVV_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base address %p is not 16-byte aligned", base);
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   IVV_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
   return 0;

@@ -300,13 +300,13 @@ extern "C" int ivv_attention(const void* q, int64_t q_ld, const void* k, const v
   {
     const uint64_t dims[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)s_q, (uint64_t)n_batch};
     const uint64_t str[4] = {2, (uint64_t)d * 2, (uint64_t)q_ld * 2, (uint64_t)q_ld * 2 * s_q};
-    if (int rc = make_tmap_f16(&tq, q, 4, dims, str, box, true)) return rc;
+    if (int rc = make_tmap_f16(&tq, q, 4, dims, str, box, 128)) return rc;
   }
   {
     const uint64_t dims[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)s_kv, (uint64_t)(n_batch / kv_div)};
     const uint64_t str[4] = {2, (uint64_t)d * 2, (uint64_t)kv_ld * 2, (uint64_t)kv_ld * 2 * s_kv};
-    if (int rc = make_tmap_f16(&tk, k, 4, dims, str, box, true)) return rc;
-    if (int rc = make_tmap_f16(&tv, v, 4, dims, str, box, true)) return rc;
+    if (int rc = make_tmap_f16(&tk, k, 4, dims, str, box, 128)) return rc;
+    if (int rc = make_tmap_f16(&tv, v, 4, dims, str, box, 128)) return rc;
   }
   dim3 grid((unsigned)((s_q + kQ - 1) / kQ), (unsigned)heads, (unsigned)n_batch);
   const int dc = (d + 63) / 64;

@@ -29,9 +29,9 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 // host: encode a tiled TMA descriptor for an fp16 tensor (rank <= 5). dims/strides innermost-first,
-// strides in BYTES for dims 1..rank-1 (dim 0 is contiguous). swizzle128 selects SWIZZLE_128B.
+// strides in BYTES for dims 1..rank-1 (dim 0 is contiguous). swizzle_bytes: 0 (none), 32, 64 or 128.
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                  const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+                  const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
 // ---------------------------------------------------------------------------------------------
 // device helpers
@@ -123,6 +123,27 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       "[%2];" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+
+// ---- TMA store (smem -> global, bulk async group) ----
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+          reinterpret_cast<uint64_t>(m)),
+      "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // ---- TMEM allocation ----
@@ -219,6 +240,19 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 // ---- small math ----
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below the fp16 output rounding): 1 rcp + 1 ex2 + 7 FMA
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __fdividef(1.f, fmaf(0.3275911f, ax, 1.f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = __expf(-ax * ax);
+  const float r = 1.f - poly * t * e;
+  return copysignf(r, x);
+}
+__device__ __forceinline__ float gelu_fast_f(float x) { return 0.5f * x * (1.f + erf_fast(x * 0.70710678118654752f)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -276,6 +276,272 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// v2: persistent kernel. One CTA per SM walks the tile list; the fp32 accumulator is double-buffered in TMEM so the
+// epilogue of tile i (8 warps: TMEM -> regs -> bias/temb/residual/GEGLU -> fp16 -> swizzled smem -> TMA store, fully
+// coalesced and clipped by the tensor map) overlaps the TMA/MMA main loop of tile i+1. Used for fp16 outputs whose row
+// stride is a multiple of 16 bytes (everything in the UNet/VAE except the 4- and 3-channel fp32 heads).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kPersistThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two groups of 4)
+
+template <int BN>
+constexpr uint32_t acc_stride_for() {
+  return BN <= 32 ? 32u : BN <= 64 ? 64u : BN <= 128 ? 128u : 256u;
+}
+template <int BN, int STAGES, int CW>
+constexpr int persist_smem_bytes() {
+  return STAGES * (kABytes + BN * 128) + 2 * (kBlockM * CW * 2) + 256;
+}
+
+template <int BN, int STAGES, int CW, bool GEGLU>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                          const __grid_constant__ CUtensorMap tmD, const __grid_constant__ GemmKParams p,
+                          int n_tiles, int total_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  constexpr int kStageBytes = kABytes + BN * 128;
+  constexpr int kStagingBytes = kBlockM * CW * 2;  // one [128 rows x CW fp16] slab per epilogue group
+  constexpr uint32_t kAccStride = acc_stride_for<BN>();
+  constexpr uint32_t kTmemCols = 2 * kAccStride;
+  uint8_t* staging = smem + STAGES * kStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int its_per_tile = p.taps * p.kblocks;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 8);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===== TMA producer =====
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int ntile = tile % n_tiles;
+        const int mtile = tile / n_tiles;
+        const int tw = mtile % p.tiles_w;
+        const int th = (mtile / p.tiles_w) % p.tiles_h;
+        const int tg = mtile / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tg * p.bn;
+        for (int it = 0; it < its_per_tile; ++it) {
+          const int tap = it / p.kblocks;
+          const int kb = it - tap * p.kblocks;
+          int dy = 0, dx = 0;
+          if (p.taps == 9) {
+            dy = tap / 3 - 1;
+            dx = tap % 3 - 1;
+          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes;
+          mbar_expect_tx(&full_bar[stage], kStageBytes);
+          tma_load_4d(sa, &tmA, &full_bar[stage], kb * kBlockK, w0 + dx, h0 + dy, n0);
+          tma_load_3d(sa + kABytes, &tmB, &full_bar[stage], kb * kBlockK, ntile * BN, tap);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===== MMA issuer =====
+      constexpr uint32_t idesc = umma_idesc_f16(kBlockM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+        const int buf = local & 1;
+        mbar_wait(&tmem_empty_bar[buf], ((local >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + buf * kAccStride;
+        for (int it = 0; it < its_per_tile; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint64_t adesc = umma_desc_kmajor_sw128(sa);
+          const uint64_t bdesc = umma_desc_kmajor_sw128(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_f16_ss(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full_bar[buf]);
+      }
+    }
+  } else {
+    // ===== epilogue: group g = (warp-2)/4 handles column chunks g, g+2, ...; warp%4 = TMEM lane quarter =====
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const bool issuer = (warp == 2 + 4 * g) && (lane == 0);
+    uint8_t* stg = staging + g * kStagingBytes;
+    const int wi = r % p.bw;
+    const int hi = (r / p.bw) % p.bh;
+    const int ni = r / (p.bw * p.bh);
+    constexpr int OUT_W = GEGLU ? BN / 2 : BN;  // output columns per tile
+    constexpr int NCHUNK = OUT_W / CW;
+    constexpr int VPR = CW / 8;                 // 16-byte vectors per staging row
+    const bool r_vec = p.residual && (p.res_ld % 8) == 0 && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int ntile = tile % n_tiles;
+      const int mtile = tile / n_tiles;
+      const int tw = mtile % p.tiles_w;
+      const int th = (mtile / p.tiles_w) % p.tiles_h;
+      const int tg = mtile / (p.tiles_w * p.tiles_h);
+      const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tg * p.bn;
+      const int w = w0 + wi, h = h0 + hi, n = n0 + ni;
+      const bool valid = (w < p.W) && (h < p.H) && (n < p.NI);
+      const long long pix = (static_cast<long long>(n) * p.H + h) * p.W + w;
+      const __half* rb = (p.rowbias && valid) ? p.rowbias + (pix / p.rowbias_group) * p.rowbias_ld : nullptr;
+      const int buf = local & 1;
+      mbar_wait(&tmem_full_bar[buf], (local >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + buf * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int chunk = g; chunk < NCHUNK; chunk += 2) {
+        const int c0 = chunk * CW;                                   // column inside the tile's output window
+        const int ocol0 = ntile * OUT_W + c0;                        // global output column
+        float v[CW];
+        if constexpr (!GEGLU) {
+#pragma unroll
+          for (int s = 0; s < CW; s += 32) {
+            uint32_t acc[32];
+            tmem_ld32(taddr + c0 + s, acc);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[s + j] = __uint_as_float(acc[j]);
+          }
+          if (chunk + 2 >= NCHUNK) {  // last chunk of this warp: the accumulator can be handed back to the MMA warp
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+          }
+#pragma unroll
+          for (int s = 0; s < CW; s += 8) {
+            const int col = ocol0 + s;
+            if (col < p.n_out) {
+              const int nv = min(8, p.n_out - col);
+              if (p.bias) {
+                float bv[8];
+                load8h(p.bias + col, nv, true, bv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[s + j] += bv[j];
+              }
+              if (rb) {
+                float bv[8];
+                load8h(rb + col, nv, (reinterpret_cast<uintptr_t>(rb + col) & 15) == 0, bv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[s + j] += bv[j];
+              }
+              if (p.residual && valid) {
+                float rv[8];
+                load8h(p.residual + pix * p.res_ld + col, nv, r_vec, rv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[s + j] += rv[j];
+              }
+            }
+          }
+        } else {
+          constexpr int HALF = BN / 2;
+#pragma unroll
+          for (int s = 0; s < CW; s += 32) {
+            uint32_t hacc[32], gacc[32];
+            tmem_ld32(taddr + c0 + s, hacc);
+            tmem_ld32(taddr + HALF + c0 + s, gacc);
+            tmem_ld_wait();
+            const int bcol = ntile * BN + c0 + s;  // interleaved bias order: [64 hidden | 64 gate] per tile
+#pragma unroll
+            for (int j8 = 0; j8 < 32; j8 += 8) {
+              float hb[8], gb[8];
+              if (p.bias) {
+                load8h(p.bias + bcol + j8, 8, true, hb);
+                load8h(p.bias + bcol + HALF + j8, 8, true, gb);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) hb[j] = gb[j] = 0.f;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float hv = __uint_as_float(hacc[j8 + j]) + hb[j];
+                const float gv = __uint_as_float(gacc[j8 + j]) + gb[j];
+                v[s + j8 + j] = hv * gelu_fast_f(gv);
+              }
+            }
+          }
+          if (chunk + 2 >= NCHUNK) {
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+          }
+        }
+        // ---- staging slab of this group: wait until its previous TMA store has finished reading it ----
+        if (issuer) bulk_wait_group_read<0>();
+        named_bar_sync(1 + g, 128);
+        uint8_t* srow = stg + r * (CW * 2);
+#pragma unroll
+        for (int cc = 0; cc < VPR; ++cc) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            __half2 hh = __floats2half2_rn(v[cc * 8 + 2 * t], v[cc * 8 + 2 * t + 1]);
+            pk[t] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+          // CW=64: 128-byte rows, SWIZZLE_128B (chunk ^ (row & 7)); CW=32: 64-byte rows, SWIZZLE_64B (chunk ^ ((row>>1)&3))
+          const int sw = (CW == 64) ? (cc ^ (r & 7)) : (cc ^ ((r >> 1) & 3));
+          *reinterpret_cast<uint4*>(srow + (sw << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1 + g, 128);
+        if (issuer) {
+          tma_store_4d(&tmD, stg, ocol0, w0, h0, n0);
+          bulk_commit_group();
+        }
+      }
+      if (NCHUNK == 1 && g == 1) {  // this group had no chunk: still release the accumulator
+        tc_fence_before();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      }
+    }
+    if (issuer) bulk_wait_group<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 static int pow2_floor_div(long long x, int cap) {
@@ -307,6 +573,34 @@ static void choose_box(long long W, long long H, long long NI, int* bw, int* bh,
   }
   (void)pow2_floor_div;
   (void)pow2_ceil;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      n = 148;
+  }
+  return n;
+}
+
+template <int BN, int STAGES, int CW, bool GEGLU>
+static int launch_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
+                             const GemmKParams& kp, int m_tiles, int n_tiles, cudaStream_t stream) {
+  constexpr int smem = persist_smem_bytes<BN, STAGES, CW>();
+  static bool configured = false;
+  if (!configured) {
+    IVV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel<BN, STAGES, CW, GEGLU>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int total = m_tiles * n_tiles;
+  const int grid = total < sm_count() ? total : sm_count();
+  gemm_tc_persistent_kernel<BN, STAGES, CW, GEGLU><<<grid, kPersistThreads, smem, stream>>>(tmA, tmB, tmD, kp, n_tiles,
+                                                                                          total);
+  IVV_CHECK_CUDA(cudaGetLastError());
+  return 0;
 }
 
 template <int BN, int STAGES>
@@ -402,15 +696,34 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
     const uint64_t strides[4] = {2, (uint64_t)a->a_ld * 2, (uint64_t)a->a_ld * 2 * a->w,
                                  (uint64_t)a->a_ld * 2 * a->w * a->h};
     const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)kp.bw, (uint32_t)kp.bh, (uint32_t)kp.bn};
-    if (int rc = make_tmap_f16(&tmA, a->a, 4, dims, strides, box, true)) return rc;
+    if (int rc = make_tmap_f16(&tmA, a->a, 4, dims, strides, box, 128)) return rc;
   }
   {
     const uint64_t dims[3] = {(uint64_t)a->c, (uint64_t)a->n_out, (uint64_t)a->taps};
     const uint64_t strides[3] = {2, (uint64_t)a->w_ld * 2, (uint64_t)a->w_ld * 2 * a->n_out};
     const uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)bn_sel, 1};
-    if (int rc = make_tmap_f16(&tmB, a->wgt, 3, dims, strides, box, true)) return rc;
+    if (int rc = make_tmap_f16(&tmB, a->wgt, 3, dims, strides, box, 128)) return rc;
   }
 
+  const bool persistent = !a->out_f32 && (a->d_ld % 8) == 0 && ((reinterpret_cast<uintptr_t>(a->d) & 15) == 0) &&
+                          (long long)m_tiles * n_tiles < (1LL << 30);
+  if (persistent) {
+    const int cw = a->geglu ? 32 : (bn_sel == 256 || bn_sel == 128) ? 64 : 32;
+    CUtensorMap tmD;
+    const uint64_t dims[4] = {(uint64_t)kp.out_cols, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n_img};
+    const uint64_t strides[4] = {2, (uint64_t)a->d_ld * 2, (uint64_t)a->d_ld * 2 * a->w,
+                                 (uint64_t)a->d_ld * 2 * a->w * a->h};
+    const uint32_t box[4] = {(uint32_t)cw, (uint32_t)kp.bw, (uint32_t)kp.bh, (uint32_t)kp.bn};
+    if (int rc = make_tmap_f16(&tmD, a->d, 4, dims, strides, box, cw == 64 ? 128 : 64)) return rc;
+    if (a->geglu) return launch_persistent<128, 6, 32, true>(tmA, tmB, tmD, kp, m_tiles, n_tiles, stream);
+    switch (bn_sel) {
+      case 256: return launch_persistent<256, 4, 64, false>(tmA, tmB, tmD, kp, m_tiles, n_tiles, stream);
+      case 160: return launch_persistent<160, 5, 32, false>(tmA, tmB, tmD, kp, m_tiles, n_tiles, stream);
+      case 128: return launch_persistent<128, 6, 64, false>(tmA, tmB, tmD, kp, m_tiles, n_tiles, stream);
+      case 64: return launch_persistent<64, 6, 32, false>(tmA, tmB, tmD, kp, m_tiles, n_tiles, stream);
+      default: return launch_persistent<32, 6, 32, false>(tmA, tmB, tmD, kp, m_tiles, n_tiles, stream);
+    }
+  }
   switch (bn_sel) {
     case 256: return launch<256, 4>(tmA, tmB, kp, m_tiles, n_tiles, stream);
     case 160: return launch<160, 3>(tmA, tmB, kp, m_tiles, n_tiles, stream);

@@ -1,106 +1,169 @@
 // GroupNorm(+SiLU) and LayerNorm(+positional encoding) for channels-last fp16 activations. HBM-bound kernels:
-// 16-byte vector loads, fp32 per-thread partials, double-precision cross-CTA merge (statistics match the fp32
-// reference to ~1e-7). Reference call sites: ivv.h (K6/K7/K8).
+// 16-byte vector loads, fp32 per-thread partials, deterministic double-precision cross-CTA merge (statistics match
+// the fp32 reference to ~1e-7). Reference call sites: ivv.h (K6/K7/K8).
 #include "../../include/ivv.h"
 #include "common.cuh"
 
 namespace ivv {
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm pass 1: per (batch-group, channel-group) sum and sum of squares
-//   x: [n_bg, rows_per_bg, C]; thread owns one 8-channel vector column and strides over rows.
+// GroupNorm pass 1: per (batch-group, channel-group) mean / rstd.
+//   x: [n_bg, rows_per_bg, C]; a thread owns one 8-channel vector column and strides over rows (4 loads in flight).
+//   Deterministic: per-CTA partials are reduced in a fixed order inside the CTA, written to the workspace, and the
+//   LAST CTA of each batch-group (atomic ticket) sums them in chunk order in double precision.
+// workspace: [counters u32 x n_bg (256-B padded)] [final float2 x n_bg x G] [partials float2 x n_bg x max_chunks x G]
 // ------------------------------------------------------------------------------------------------
-__global__ void gn_stats_kernel(const __half* __restrict__ x, double* __restrict__ stats, long long rows_per_bg, int C,
-                                int groups, long long rows_per_cta, int V, int R) {
-  __shared__ float s_acc[64 * 2];  // groups <= 64
+struct GnWs {
+  unsigned int* counters;
+  float2* final_;   // (mean, rstd)
+  float2* partial;  // (sum, sumsq)
+  int max_chunks;
+};
+__host__ __device__ inline int gn_max_chunks(long long n_bg) { return (int)(148 * 4 / n_bg) + 2; }
+__host__ __device__ inline size_t gn_counter_bytes(long long n_bg) { return (size_t)((n_bg * 4 + 255) / 256 * 256); }
+
+__global__ void gn_stats_kernel(const __half* __restrict__ x, GnWs ws, long long rows_per_bg, int C, int groups,
+                                long long rows_per_cta, int V, int R, float eps) {
+  extern __shared__ float s_part[];  // [R][C][2]
+  __shared__ float s_grp[64 * 2];
+  __shared__ bool s_last;
   const int bg = blockIdx.y;
+  const int chunks = gridDim.x;
   const long long row_begin = (long long)blockIdx.x * rows_per_cta;
   const long long row_end = min(rows_per_bg, row_begin + rows_per_cta);
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
   const int vec = threadIdx.x % V;
   const int rsub = threadIdx.x / V;
+  const int cpg = C / groups;
   float s[8], ss[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
   if (rsub < R) {
     const __half* base = x + ((long long)bg * rows_per_bg) * C + vec * 8;
-    for (long long r = row_begin + rsub; r < row_end; r += R) {
+    long long r = row_begin + rsub;
+    for (; r + 3LL * R < row_end; r += 4LL * R) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(base + (r + (long long)k * R) * C);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const __half2* h = reinterpret_cast<const __half2*>(&u[k]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h[j]);
+          s[2 * j] += f.x;
+          ss[2 * j] = fmaf(f.x, f.x, ss[2 * j]);
+          s[2 * j + 1] += f.y;
+          ss[2 * j + 1] = fmaf(f.y, f.y, ss[2 * j + 1]);
+        }
+      }
+    }
+    for (; r < row_end; r += R) {
       const uint4 u = *reinterpret_cast<const uint4*>(base + r * C);
       const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 f = __half22float2(h[j]);
         s[2 * j] += f.x;
-        ss[2 * j] += f.x * f.x;
+        ss[2 * j] = fmaf(f.x, f.x, ss[2 * j]);
         s[2 * j + 1] += f.y;
-        ss[2 * j + 1] += f.y * f.y;
+        ss[2 * j + 1] = fmaf(f.y, f.y, ss[2 * j + 1]);
       }
     }
-    const int cpg = C / groups;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const int g = (vec * 8 + j) / cpg;
-      atomicAdd(&s_acc[2 * g], s[j]);
-      atomicAdd(&s_acc[2 * g + 1], ss[j]);
+      s_part[((rsub * C) + vec * 8 + j) * 2] = s[j];
+      s_part[((rsub * C) + vec * 8 + j) * 2 + 1] = ss[j];
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x)
-    atomicAdd(&stats[(long long)bg * groups * 2 + i], (double)s_acc[i]);
+  // fixed-order in-CTA reduction: thread g sums its group's channels over all row lanes
+  if (threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    float a = 0.f, b = 0.f;
+    for (int rr = 0; rr < R; ++rr)
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        a += s_part[(rr * C + c) * 2];
+        b += s_part[(rr * C + c) * 2 + 1];
+      }
+    ws.partial[((long long)bg * ws.max_chunks + blockIdx.x) * groups + g] = make_float2(a, b);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&ws.counters[bg], 1u);
+    s_last = (t == (unsigned int)chunks - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < groups) {
+    const int g = threadIdx.x;
+    double a = 0.0, b = 0.0;
+    for (int ch = 0; ch < chunks; ++ch) {
+      const float2 pv = __ldcg(&ws.partial[((long long)bg * ws.max_chunks + ch) * groups + g]);
+      a += (double)pv.x;
+      b += (double)pv.y;
+    }
+    const double inv_n = 1.0 / ((double)rows_per_bg * cpg);
+    const double mean = a * inv_n;
+    double var = b * inv_n - mean * mean;
+    if (var < 0) var = 0;
+    ws.final_[(long long)bg * groups + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+  }
+  (void)s_grp;
 }
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm pass 2: y = (x - mean) * rstd * gamma + beta, optional SiLU
+// GroupNorm pass 2: y = (x - mean) * rstd * gamma + beta, optional SiLU. Same thread->column mapping as pass 1:
+// the 8 scale/shift pairs of a thread are loop invariants held in registers.
 // ------------------------------------------------------------------------------------------------
 __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y, const __half* __restrict__ gamma,
-                                const __half* __restrict__ beta, const double* __restrict__ stats,
-                                long long rows_per_bg, int C, int groups, float eps, int silu, long long rows_per_cta) {
-  extern __shared__ float s_ab[];  // a[C], b[C]
-  float* s_a = s_ab;
-  float* s_b = s_ab + C;
+                                const __half* __restrict__ beta, const float2* __restrict__ final_,
+                                long long rows_per_bg, int C, int groups, int silu, long long rows_per_cta, int V,
+                                int R) {
   const int bg = blockIdx.y;
+  const int vec = threadIdx.x % V;
+  const int rsub = threadIdx.x / V;
+  if (rsub >= R) return;
   const int cpg = C / groups;
-  const double inv_n = 1.0 / ((double)rows_per_bg * cpg);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const double sum = stats[((long long)bg * groups + g) * 2];
-    const double sq = stats[((long long)bg * groups + g) * 2 + 1];
-    const double mean = sum * inv_n;
-    double var = sq * inv_n - mean * mean;
-    if (var < 0) var = 0;
-    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-    const float a = rstd * __half2float(gamma[c]);
-    s_a[c] = a;
-    s_b[c] = __half2float(beta[c]) - (float)mean * a;
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = vec * 8 + j;
+    const float2 mr = final_[(long long)bg * groups + c / cpg];
+    a[j] = mr.y * __half2float(gamma[c]);
+    b[j] = __half2float(beta[c]) - mr.x * a[j];
   }
-  __syncthreads();
-  const int V = C / 8;
   const long long row_begin = (long long)blockIdx.x * rows_per_cta;
   const long long row_end = min(rows_per_bg, row_begin + rows_per_cta);
-  const long long total = (row_end - row_begin) * V;
-  const __half* xb = x + ((long long)bg * rows_per_bg + row_begin) * C;
-  __half* yb = y + ((long long)bg * rows_per_bg + row_begin) * C;
-  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
-    const int vec = (int)(i % V);
-    const uint4 u = *reinterpret_cast<const uint4*>(xb + i * 8);
+  const __half* xb = x + ((long long)bg * rows_per_bg) * C + vec * 8;
+  __half* yb = y + ((long long)bg * rows_per_bg) * C + vec * 8;
+  auto xform = [&](const uint4& u) {
     const __half2* h = reinterpret_cast<const __half2*>(&u);
     uint4 o;
     __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 f = __half22float2(h[j]);
-      const int c = vec * 8 + 2 * j;
-      float v0 = f.x * s_a[c] + s_b[c];
-      float v1 = f.y * s_a[c + 1] + s_b[c + 1];
+      float v0 = fmaf(f.x, a[2 * j], b[2 * j]);
+      float v1 = fmaf(f.y, a[2 * j + 1], b[2 * j + 1]);
       if (silu) {
         v0 = silu_f(v0);
         v1 = silu_f(v1);
       }
       oh[j] = __floats2half2_rn(v0, v1);
     }
-    *reinterpret_cast<uint4*>(yb + i * 8) = o;
+    return o;
+  };
+  long long r = row_begin + rsub;
+  for (; r + 3LL * R < row_end; r += 4LL * R) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(xb + (r + (long long)k * R) * C);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(yb + (r + (long long)k * R) * C) = xform(u[k]);
   }
+  for (; r < row_end; r += R) *reinterpret_cast<uint4*>(yb + r * C) = xform(*reinterpret_cast<const uint4*>(xb + r * C));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -214,8 +277,11 @@ __global__ void softmax_rows_kernel(const TIn* __restrict__ x, __half* __restric
 }  // namespace ivv
 
 extern "C" size_t ivv_groupnorm_ws_bytes(int64_t n_img, int32_t groups, int64_t frames_per_group) {
-  if (frames_per_group <= 0) return 0;
-  return (size_t)(n_img / frames_per_group) * groups * 2 * sizeof(double);
+  if (frames_per_group <= 0 || groups <= 0) return 0;
+  const long long n_bg = n_img / frames_per_group;
+  if (n_bg <= 0) return 0;
+  return ivv::gn_counter_bytes(n_bg) + (size_t)n_bg * groups * sizeof(float2) +
+         (size_t)n_bg * ivv::gn_max_chunks(n_bg) * groups * sizeof(float2);
 }
 
 extern "C" int ivv_groupnorm(const void* x, void* y, const void* gamma, const void* beta, int64_t n_img, int64_t hw,
@@ -233,37 +299,47 @@ extern "C" int ivv_groupnorm(const void* x, void* y, const void* gamma, const vo
   IVV_REQUIRE(c % 8 == 0 && c <= 8192, "ivv_groupnorm: c (%lld) must be a multiple of 8 and <= 8192", (long long)c);
   const size_t need = ivv_groupnorm_ws_bytes(n_img, groups, frames_per_group);
   IVV_REQUIRE(stats_ws_bytes >= need, "ivv_groupnorm: workspace too small (%zu < %zu)", stats_ws_bytes, need);
+  IVV_REQUIRE((reinterpret_cast<uintptr_t>(stats_ws) & 15) == 0, "ivv_groupnorm: workspace must be 16-byte aligned");
   const long long n_bg = n_img / frames_per_group;
   const long long rows_per_bg = frames_per_group * hw;
   IVV_REQUIRE(n_bg <= 65535, "ivv_groupnorm: too many batch groups");
-  IVV_CHECK_CUDA(cudaMemsetAsync(stats_ws, 0, need, stream));
+  GnWs ws;
+  ws.counters = reinterpret_cast<unsigned int*>(stats_ws);
+  ws.final_ = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(stats_ws) + gn_counter_bytes(n_bg));
+  ws.partial = ws.final_ + n_bg * groups;
+  ws.max_chunks = gn_max_chunks(n_bg);
+  IVV_CHECK_CUDA(cudaMemsetAsync(stats_ws, 0, gn_counter_bytes(n_bg), stream));
   const int V = (int)(c / 8);
   const int R = V >= 256 ? 1 : 256 / V;
   const int threads = V * R;
-  // ~4 CTAs per SM in total, but at least 8 row sweeps per CTA
-  long long chunks = (148 * 4 + n_bg - 1) / n_bg;
-  long long rows_per_cta = (rows_per_bg + chunks - 1) / chunks;
-  if (rows_per_cta < 8LL * R) rows_per_cta = 8LL * R;
-  chunks = (rows_per_bg + rows_per_cta - 1) / rows_per_cta;
   {
+    // ~4 CTAs per SM in total, at least 8 row sweeps per CTA, never more chunks than the workspace holds
+    long long chunks = (148 * 4 + n_bg - 1) / n_bg;
+    long long rows_per_cta = (rows_per_bg + chunks - 1) / chunks;
+    if (rows_per_cta < 8LL * R) rows_per_cta = 8LL * R;
+    chunks = (rows_per_bg + rows_per_cta - 1) / rows_per_cta;
+    IVV_REQUIRE(chunks <= ws.max_chunks, "ivv_groupnorm: internal chunking error");
     dim3 grid((unsigned)chunks, (unsigned)n_bg);
-    gn_stats_kernel<<<grid, threads, 0, stream>>>(reinterpret_cast<const __half*>(x),
-                                                  reinterpret_cast<double*>(stats_ws), rows_per_bg, (int)c, groups,
-                                                  rows_per_cta, V, R);
+    const size_t smem = (size_t)R * c * 2 * sizeof(float);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      IVV_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      configured = 96 * 1024;
+    }
+    gn_stats_kernel<<<grid, threads, smem, stream>>>(reinterpret_cast<const __half*>(x), ws, rows_per_bg, (int)c,
+                                                     groups, rows_per_cta, V, R, eps);
     IVV_CHECK_CUDA(cudaGetLastError());
   }
   {
     long long chunks2 = (148 * 8 + n_bg - 1) / n_bg;
     long long rpc = (rows_per_bg + chunks2 - 1) / chunks2;
-    if (rpc < 16) rpc = 16;
+    if (rpc < 4LL * R) rpc = 4LL * R;
     chunks2 = (rows_per_bg + rpc - 1) / rpc;
     dim3 grid((unsigned)chunks2, (unsigned)n_bg);
-    const size_t smem = (size_t)c * 2 * sizeof(float);
-    gn_apply_kernel<<<grid, 256, smem, stream>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y),
-                                                 reinterpret_cast<const __half*>(gamma),
-                                                 reinterpret_cast<const __half*>(beta),
-                                                 reinterpret_cast<const double*>(stats_ws), rows_per_bg, (int)c, groups,
-                                                 eps, silu, rpc);
+    gn_apply_kernel<<<grid, threads, 0, stream>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y),
+                                                  reinterpret_cast<const __half*>(gamma),
+                                                  reinterpret_cast<const __half*>(beta), ws.final_, rows_per_bg, (int)c,
+                                                  groups, silu, rpc, V, R);
     IVV_CHECK_CUDA(cudaGetLastError());
   }
   return 0;
