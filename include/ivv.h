@@ -39,7 +39,7 @@ typedef struct {
   const void* wgt;    /* fp16 [taps][n_out][w_ld]  (w_ld >= c, multiple of 8, zero padded)                     */
   int64_t n_out, w_ld;
   int32_t taps;       /* 1 or 9                                                                                */
-  int32_t geglu;      /* 1: weight rows are tile-interleaved [64 hidden | 64 gate]; output width n_out/2        */
+  int32_t geglu;      /* 1: weight rows are tile-interleaved [128 hidden | 128 gate]; output width n_out/2      */
   void* d;            /* fp16 (or fp32 when out_f32) [n_img*h*w, d_ld]                                         */
   int64_t d_ld;
   int32_t out_f32;

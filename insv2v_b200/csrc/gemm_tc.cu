@@ -431,6 +431,23 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         const int c0 = chunk * CW;                                   // column inside the tile's output window
         const int ocol0 = ntile * OUT_W + c0;                        // global output column
         float v[CW];
+        // coalesced residual prefetch: lane l fetches 16-byte vector (l % VPR) of rows (l / VPR) + k*(32/VPR) of this
+        // warp's 32 rows, so every load instruction covers whole 128-byte (64-byte) row segments; the vectors are
+        // handed to their owner rows through the staging slab below.
+        uint4 rres[VPR];
+        const bool res_co = !GEGLU && r_vec && (p.n_out % 8) == 0;
+        if (res_co) {
+#pragma unroll
+          for (int k = 0; k < VPR; ++k) {
+            const int rr = q * 32 + (lane / VPR) + k * (32 / VPR);
+            const int w2 = w0 + (rr % p.bw), h2 = h0 + ((rr / p.bw) % p.bh), n2 = n0 + rr / (p.bw * p.bh);
+            const int col = ocol0 + (lane % VPR) * 8;
+            rres[k] = make_uint4(0, 0, 0, 0);
+            if (w2 < p.W && h2 < p.H && n2 < p.NI && col < p.n_out)
+              rres[k] = *reinterpret_cast<const uint4*>(
+                  p.residual + ((static_cast<long long>(n2) * p.H + h2) * p.W + w2) * p.res_ld + col);
+          }
+        }
         if constexpr (!GEGLU) {
 #pragma unroll
           for (int s = 0; s < CW; s += 32) {
@@ -461,7 +478,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[s + j] += bv[j];
               }
-              if (p.residual && valid) {
+              if (p.residual && valid && !res_co) {
                 float rv[8];
                 load8h(p.residual + pix * p.res_ld + col, nv, r_vec, rv);
 #pragma unroll
@@ -505,6 +522,28 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         if (issuer) bulk_wait_group_read<0>();
         named_bar_sync(1 + g, 128);
         uint8_t* srow = stg + r * (CW * 2);
+        if (res_co) {
+#pragma unroll
+          for (int k = 0; k < VPR; ++k) {
+            const int rr = q * 32 + (lane / VPR) + k * (32 / VPR);
+            const int cc = lane % VPR;
+            const int sw = (CW == 64) ? (cc ^ (rr & 7)) : (cc ^ ((rr >> 1) & 3));
+            *reinterpret_cast<uint4*>(stg + rr * (CW * 2) + (sw << 4)) = rres[k];
+          }
+          __syncwarp();
+#pragma unroll
+          for (int cc = 0; cc < VPR; ++cc) {
+            const int sw = (CW == 64) ? (cc ^ (r & 7)) : (cc ^ ((r >> 1) & 3));
+            const uint4 u = *reinterpret_cast<const uint4*>(srow + (sw << 4));
+            const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 f = __half22float2(hh[t]);
+              v[cc * 8 + 2 * t] += f.x;
+              v[cc * 8 + 2 * t + 1] += f.y;
+            }
+          }
+        }
 #pragma unroll
         for (int cc = 0; cc < VPR; ++cc) {
           uint32_t pk[4];
@@ -630,7 +669,7 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
   IVV_REQUIRE(a->a_ld % 8 == 0 && a->w_ld % 8 == 0, "ivv_gemm: a_ld (%lld) and w_ld (%lld) must be multiples of 8",
               (long long)a->a_ld, (long long)a->w_ld);
   IVV_REQUIRE(a->c <= a->a_ld && a->c <= a->w_ld, "ivv_gemm: c exceeds a leading dimension");
-  IVV_REQUIRE(!a->geglu || (a->n_out % 128 == 0), "ivv_gemm: GEGLU needs n_out %% 128 == 0");
+  IVV_REQUIRE(!a->geglu || (a->n_out % 256 == 0), "ivv_gemm: GEGLU needs n_out %% 256 == 0");
   IVV_REQUIRE(!(a->geglu && (a->rowbias || a->residual)), "ivv_gemm: GEGLU epilogue takes bias only");
 
   GemmKParams kp{};
@@ -662,7 +701,7 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
   // ---- tile-N choice: least padding first, then enough CTAs to fill 148 SMs ----
   int bn_sel;
   if (a->geglu) {
-    bn_sel = 128;
+    bn_sel = 256;
   } else {
     const int cands[5] = {256, 160, 128, 64, 32};
     double best_waste = 1e9;
@@ -715,7 +754,7 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
                                  (uint64_t)a->d_ld * 2 * a->w * a->h};
     const uint32_t box[4] = {(uint32_t)cw, (uint32_t)kp.bw, (uint32_t)kp.bh, (uint32_t)kp.bn};
     if (int rc = make_tmap_f16(&tmD, a->d, 4, dims, strides, box, cw == 64 ? 128 : 64)) return rc;
-    if (a->geglu) return launch_persistent<128, 6, 32, true>(tmA, tmB, tmD, kp, m_tiles, n_tiles, stream);
+    if (a->geglu) return launch_persistent<256, 4, 32, true>(tmA, tmB, tmD, kp, m_tiles, n_tiles, stream);
     switch (bn_sel) {
       case 256: return launch_persistent<256, 4, 64, false>(tmA, tmB, tmD, kp, m_tiles, n_tiles, stream);
       case 160: return launch_persistent<160, 5, 32, false>(tmA, tmB, tmD, kp, m_tiles, n_tiles, stream);

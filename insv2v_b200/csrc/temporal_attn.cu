@@ -114,6 +114,145 @@ __global__ void temporal_attn_kernel(const __half* __restrict__ qkv, __half* __r
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// frames <= 16: one WARP per (pixel, head) on the legacy tensor-core path (mma.sync m16n8k16, fp32 accumulate): the
+// 16 x 16 score tile is exactly one MMA row block, so the kernel is purely memory bound (11 MMAs per head at d = 40).
+// S = Q K^T: A fragments are plain 32-bit loads of Q rows, B fragments plain 32-bit loads of K rows;
+// O = P V: the S accumulator registers ARE the A fragments of P; V is fetched with ldmatrix.trans.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                          uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void temporal_attn_mma_kernel(const __half* __restrict__ qkv, __half* __restrict__ o, int frames,
+                                         long long hw, int C, int heads, int heads_per_cta, float scale) {
+  extern __shared__ __align__(16) uint8_t smem_t[];
+  __half* s = reinterpret_cast<__half*>(smem_t);
+  const int d = C / heads;
+  const int seg = heads_per_cta * d;
+  const int row_ld = 3 * seg + kTPad;
+  const long long bp = blockIdx.x;
+  const long long clip = bp / hw, pix = bp % hw;
+  const int head0 = blockIdx.y * heads_per_cta;
+  const int vec_per_seg = seg / 8;
+  const int total_vec = 16 * 3 * vec_per_seg;  // rows >= frames are zero-filled
+  for (int i = threadIdx.x; i < total_vec; i += blockDim.x) {
+    const int v = i % vec_per_seg;
+    const int part = (i / vec_per_seg) % 3;
+    const int f = i / (3 * vec_per_seg);
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (f < frames) {
+      const long long row = (clip * frames + f) * hw + pix;
+      u = *reinterpret_cast<const uint4*>(qkv + row * 3 * C + (long long)part * C + head0 * d + v * 8);
+    }
+    *reinterpret_cast<uint4*>(s + f * row_ld + part * seg + v * 8) = u;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp < heads_per_cta) {
+    const int gid = lane >> 2, tig = lane & 3;
+    __half* qb = s + warp * d;
+    const __half* kb = s + seg + warp * d;
+    const __half* vb = s + 2 * seg + warp * d;
+    float sacc[2][4];
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sacc[t][j] = 0.f;
+    const int ksteps = (d + 15) / 16;
+    for (int ks = 0; ks < ksteps; ++ks) {
+      const int c_lo = ks * 16 + 2 * tig, c_hi = c_lo + 8;
+      const bool lo_ok = c_lo < d, hi_ok = c_hi < d;  // d % 8 == 0: a pair never straddles the head boundary
+      const uint32_t a0 = lo_ok ? *reinterpret_cast<const uint32_t*>(qb + gid * row_ld + c_lo) : 0u;
+      const uint32_t a1 = lo_ok ? *reinterpret_cast<const uint32_t*>(qb + (gid + 8) * row_ld + c_lo) : 0u;
+      const uint32_t a2 = hi_ok ? *reinterpret_cast<const uint32_t*>(qb + gid * row_ld + c_hi) : 0u;
+      const uint32_t a3 = hi_ok ? *reinterpret_cast<const uint32_t*>(qb + (gid + 8) * row_ld + c_hi) : 0u;
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const __half* kr = kb + (t * 8 + gid) * row_ld;
+        const uint32_t b0 = lo_ok ? *reinterpret_cast<const uint32_t*>(kr + c_lo) : 0u;
+        const uint32_t b1 = hi_ok ? *reinterpret_cast<const uint32_t*>(kr + c_hi) : 0u;
+        mma_16816(sacc[t], a0, a1, a2, a3, b0, b1);
+      }
+    }
+    // softmax over the 16 keys of rows gid (regs 0,1) and gid+8 (regs 2,3); keys >= frames are masked
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const bool ok = (t * 8 + 2 * tig + j) < frames;
+        sacc[t][j] = ok ? sacc[t][j] * scale : -INFINITY;
+        sacc[t][2 + j] = ok ? sacc[t][2 + j] * scale : -INFINITY;
+        m0 = fmaxf(m0, sacc[t][j]);
+        m1 = fmaxf(m1, sacc[t][2 + j]);
+      }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 2; ++t)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        sacc[t][j] = __expf(sacc[t][j] - m0);
+        sacc[t][2 + j] = __expf(sacc[t][2 + j] - m1);
+        l0 += sacc[t][j];
+        l1 += sacc[t][2 + j];
+      }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    // P (fp16) as the A operand of O = P V (k = key index)
+    const uint32_t p0 = pack_h2(sacc[0][0], sacc[0][1]), p1 = pack_h2(sacc[0][2], sacc[0][3]);
+    const uint32_t p2 = pack_h2(sacc[1][0], sacc[1][1]), p3 = pack_h2(sacc[1][2], sacc[1][3]);
+    // residual of the fp16 rounding of P: a second (free, the kernel is memory bound) MMA keeps P at ~22 bits so the
+    // result meets the 1e-3 / 1e-4 tolerance against the fp32 reference
+    auto lo2 = [](float a, float b, uint32_t hi) {
+      const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+      return pack_h2(a - h.x, b - h.y);
+    };
+    const uint32_t q0 = lo2(sacc[0][0], sacc[0][1], p0), q1 = lo2(sacc[0][2], sacc[0][3], p1);
+    const uint32_t q2 = lo2(sacc[1][0], sacc[1][1], p2), q3 = lo2(sacc[1][2], sacc[1][3], p3);
+    __syncwarp();  // every lane has finished reading Q before O overwrites it
+    const int ntiles = d / 8;
+    for (int nt = 0; nt < ntiles; ++nt) {
+      // ldmatrix.trans: lanes 0-7 address V rows 0-7, lanes 8-15 rows 8-15 (column nt*8); other lanes' addresses unused
+      const __half* vaddr = vb + (lane & 15) * row_ld + nt * 8;
+      uint32_t b0, b1;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];"
+                   : "=r"(b0), "=r"(b1)
+                   : "r"(smem_u32(vaddr)));
+      float oacc[4] = {0.f, 0.f, 0.f, 0.f};
+      mma_16816(oacc, q0, q1, q2, q3, b0, b1);
+      mma_16816(oacc, p0, p1, p2, p3, b0, b1);
+      *reinterpret_cast<uint32_t*>(qb + gid * row_ld + nt * 8 + 2 * tig) = pack_h2(oacc[0] * i0, oacc[1] * i0);
+      *reinterpret_cast<uint32_t*>(qb + (gid + 8) * row_ld + nt * 8 + 2 * tig) = pack_h2(oacc[2] * i1, oacc[3] * i1);
+    }
+  }
+  __syncthreads();
+  const int total_out = frames * vec_per_seg;
+  for (int i = threadIdx.x; i < total_out; i += blockDim.x) {
+    const int v = i % vec_per_seg;
+    const int f = i / vec_per_seg;
+    const long long row = (clip * frames + f) * hw + pix;
+    *reinterpret_cast<uint4*>(o + row * C + head0 * d + v * 8) = *reinterpret_cast<const uint4*>(s + f * row_ld + v * 8);
+  }
+}
+
 }  // namespace ivv
 
 extern "C" int ivv_temporal_attention(const void* qkv, void* o, int64_t clips, int64_t frames, int64_t hw, int64_t c,
@@ -125,6 +264,30 @@ extern "C" int ivv_temporal_attention(const void* qkv, void* o, int64_t clips, i
   IVV_REQUIRE(c % heads == 0 && (c / heads) % 8 == 0 && (c / heads) <= 256,
               "ivv_temporal_attention: head dim %lld must be a multiple of 8 and <= 256", (long long)(c / heads));
   const int d = (int)(c / heads);
+  const __half* in = reinterpret_cast<const __half*>(qkv);
+  __half* out = reinterpret_cast<__half*>(o);
+  const long long bp = clips * hw;
+  IVV_REQUIRE(bp < (1LL << 31), "ivv_temporal_attention: too many sequences");
+  if (frames <= 16) {
+    // tensor-core path: warp per head, <= ~32 KB of shared memory per CTA so several CTAs share an SM
+    int hpc = heads;
+    auto smem16 = [&](int h) { return (size_t)16 * (3 * h * d + kTPad) * sizeof(__half); };
+    while (hpc > 1 && (smem16(hpc) > 40 * 1024 || heads % hpc != 0)) --hpc;
+    const size_t smem = smem16(hpc);
+    IVV_REQUIRE(smem <= 200 * 1024, "ivv_temporal_attention: tile does not fit shared memory");
+    static bool configured16 = false;
+    if (!configured16) {
+      IVV_CHECK_CUDA(
+          cudaFuncSetAttribute(temporal_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured16 = true;
+    }
+    dim3 grid((unsigned)bp, (unsigned)(heads / hpc));
+    int threads = hpc * 32;
+    if (threads < 64) threads = 64;
+    temporal_attn_mma_kernel<<<grid, threads, smem, stream>>>(in, out, (int)frames, hw, (int)c, heads, hpc, scale);
+    IVV_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   int hpc = heads;
   auto smem_for = [&](int h) { return (size_t)frames * (3 * h * d + kTPad) * sizeof(__half); };
   while (hpc > 1 && (smem_for(hpc) > 96 * 1024 || heads % hpc != 0 || hpc * frames > 1024)) --hpc;
@@ -138,14 +301,10 @@ extern "C" int ivv_temporal_attention(const void* qkv, void* o, int64_t clips, i
         cudaFuncSetAttribute(temporal_attn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
-  const long long bp = clips * hw;
-  IVV_REQUIRE(bp < (1LL << 31), "ivv_temporal_attention: too many sequences");
   dim3 grid((unsigned)bp, (unsigned)(heads / hpc));
   int threads = (int)(hpc * frames);
   threads = (threads + 31) / 32 * 32;
   if (threads < 64) threads = 64;
-  const __half* in = reinterpret_cast<const __half*>(qkv);
-  __half* out = reinterpret_cast<__half*>(o);
   if (frames <= 16)
     temporal_attn_kernel<16><<<grid, threads, smem, stream>>>(in, out, (int)frames, hw, (int)c, heads, hpc, scale);
   else

