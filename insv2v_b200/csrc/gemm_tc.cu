@@ -287,28 +287,31 @@ template <int BN>
 constexpr uint32_t acc_stride_for() {
   return BN <= 32 ? 32u : BN <= 64 ? 64u : BN <= 128 ? 128u : 256u;
 }
-template <int BN, int STAGES, int CW>
+template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE>
 constexpr int persist_smem_bytes() {
-  return STAGES * (kABytes + BN * 128) + 2 * (kBlockM * CW * 2) + 256;
+  // TILEWIDE: the whole fp16 output tile is staged; otherwise one CW-wide slab per epilogue group
+  return STAGES * (kABytes + BN * 128) + (TILEWIDE ? kBlockM * (GEGLU ? BN / 2 : BN) * 2 : 2 * kBlockM * CW * 2) + 256;
 }
 
-template <int BN, int STAGES, int CW, bool GEGLU>
+template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                          const __grid_constant__ CUtensorMap tmD, const __grid_constant__ GemmKParams p,
-                          int n_tiles, int total_tiles) {
+                          const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
+                          const __grid_constant__ GemmKParams p, int n_tiles, int total_tiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   constexpr int kStageBytes = kABytes + BN * 128;
-  constexpr int kStagingBytes = kBlockM * CW * 2;  // one [128 rows x CW fp16] slab per epilogue group
+  constexpr int kChunkBytes = kBlockM * CW * 2;  // one [128 rows x CW fp16] swizzled slab per column chunk
+  constexpr int kStagingBytes = TILEWIDE ? kBlockM * (GEGLU ? BN / 2 : BN) * 2 : 2 * kChunkBytes;
   constexpr uint32_t kAccStride = acc_stride_for<BN>();
   constexpr uint32_t kTmemCols = 2 * kAccStride;
   uint8_t* staging = smem + STAGES * kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + 2 * kStagingBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* res_bar = tmem_empty_bar + 2;        // [2] residual tile landed (one per epilogue group)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -318,6 +321,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmD);
+    tma_prefetch_desc(&tmR);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -325,6 +329,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
       mbar_init(&tmem_empty_bar[b], 8);  // one arrive per epilogue warp
+      mbar_init(&res_bar[b], 1);
     }
     fence_mbar_init();
   }
@@ -402,14 +407,15 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const bool issuer = (warp == 2 + 4 * g) && (lane == 0);
-    uint8_t* stg = staging + g * kStagingBytes;
     const int wi = r % p.bw;
     const int hi = (r / p.bw) % p.bh;
     const int ni = r / (p.bw * p.bh);
     constexpr int OUT_W = GEGLU ? BN / 2 : BN;  // output columns per tile
     constexpr int NCHUNK = OUT_W / CW;
     constexpr int VPR = CW / 8;                 // 16-byte vectors per staging row
-    const bool r_vec = p.residual && (p.res_ld % 8) == 0 && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
+    const bool has_res = !GEGLU && p.residual != nullptr;
+    const int my_chunks = (NCHUNK - g + 1) / 2;  // chunks g, g+2, ...
+    uint32_t res_phase = 0;
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int ntile = tile % n_tiles;
@@ -423,31 +429,50 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       const long long pix = (static_cast<long long>(n) * p.H + h) * p.W + w;
       const __half* rb = (p.rowbias && valid) ? p.rowbias + (pix / p.rowbias_group) * p.rowbias_ld : nullptr;
       const int buf = local & 1;
+      if constexpr (TILEWIDE) {
+        // While the main loop of this tile is still running: make sure the stores of the previous tile have drained
+        // the staging slabs, then let TMA drop the residual tile straight into them (coalesced, no registers).
+        if (issuer) {
+          bulk_wait_group_read<0>();
+          if (has_res && my_chunks > 0) {
+            mbar_expect_tx(&res_bar[g], my_chunks * kChunkBytes);
+            for (int chunk = g; chunk < NCHUNK; chunk += 2)
+              tma_load_4d(staging + chunk * kChunkBytes, &tmR, &res_bar[g], ntile * OUT_W + chunk * CW, w0, h0, n0);
+          }
+        }
+        if (!has_res) named_bar_sync(1 + g, 128);
+      }
       mbar_wait(&tmem_full_bar[buf], (local >> 1) & 1);
       tc_fence_after();
+      if constexpr (TILEWIDE) {
+        if (has_res && my_chunks > 0) {
+          mbar_wait(&res_bar[g], res_phase);
+          res_phase ^= 1;
+        }
+      }
       const uint32_t taddr = tmem_base + buf * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
       for (int chunk = g; chunk < NCHUNK; chunk += 2) {
-        const int c0 = chunk * CW;                                   // column inside the tile's output window
-        const int ocol0 = ntile * OUT_W + c0;                        // global output column
-        float v[CW];
-        // coalesced residual prefetch: lane l fetches 16-byte vector (l % VPR) of rows (l / VPR) + k*(32/VPR) of this
-        // warp's 32 rows, so every load instruction covers whole 128-byte (64-byte) row segments; the vectors are
-        // handed to their owner rows through the staging slab below.
-        uint4 rres[VPR];
-        const bool res_co = !GEGLU && r_vec && (p.n_out % 8) == 0;
-        if (res_co) {
-#pragma unroll
-          for (int k = 0; k < VPR; ++k) {
-            const int rr = q * 32 + (lane / VPR) + k * (32 / VPR);
-            const int w2 = w0 + (rr % p.bw), h2 = h0 + ((rr / p.bw) % p.bh), n2 = n0 + rr / (p.bw * p.bh);
-            const int col = ocol0 + (lane % VPR) * 8;
-            rres[k] = make_uint4(0, 0, 0, 0);
-            if (w2 < p.W && h2 < p.H && n2 < p.NI && col < p.n_out)
-              rres[k] = *reinterpret_cast<const uint4*>(
-                  p.residual + ((static_cast<long long>(n2) * p.H + h2) * p.W + w2) * p.res_ld + col);
+        uint8_t* stg = TILEWIDE ? staging + chunk * kChunkBytes : staging + g * kChunkBytes;
+        const int c0 = chunk * CW;             // column inside the tile's output window
+        const int ocol0 = ntile * OUT_W + c0;  // global output column
+        if constexpr (!TILEWIDE) {
+          // ring mode: one slab per group; wait for its previous store, then fetch this chunk's residual into it
+          if (issuer) {
+            bulk_wait_group_read<0>();
+            if (has_res) {
+              mbar_expect_tx(&res_bar[g], kChunkBytes);
+              tma_load_4d(stg, &tmR, &res_bar[g], ocol0, w0, h0, n0);
+            }
+          }
+          if (has_res) {
+            mbar_wait(&res_bar[g], res_phase);
+            res_phase ^= 1;
+          } else {
+            named_bar_sync(1 + g, 128);
           }
         }
+        float v[CW];
         if constexpr (!GEGLU) {
 #pragma unroll
           for (int s = 0; s < CW; s += 32) {
@@ -478,12 +503,6 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[s + j] += bv[j];
               }
-              if (p.residual && valid && !res_co) {
-                float rv[8];
-                load8h(p.residual + pix * p.res_ld + col, nv, r_vec, rv);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[s + j] += rv[j];
-              }
             }
           }
         } else {
@@ -494,7 +513,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             tmem_ld32(taddr + c0 + s, hacc);
             tmem_ld32(taddr + HALF + c0 + s, gacc);
             tmem_ld_wait();
-            const int bcol = ntile * BN + c0 + s;  // interleaved bias order: [64 hidden | 64 gate] per tile
+            const int bcol = ntile * BN + c0 + s;  // interleaved bias order: [128 hidden | 128 gate] per tile
 #pragma unroll
             for (int j8 = 0; j8 < 32; j8 += 8) {
               float hb[8], gb[8];
@@ -518,23 +537,15 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
           }
         }
-        // ---- staging slab of this group: wait until its previous TMA store has finished reading it ----
-        if (issuer) bulk_wait_group_read<0>();
-        named_bar_sync(1 + g, 128);
+        // ---- own row of the slab: add the TMA-fetched residual, then overwrite it with the fp16 result ----
+        // CW=64: 128-byte rows, SWIZZLE_128B (chunk ^ (row & 7)); CW=32: 64-byte rows, SWIZZLE_64B (chunk ^ ((row>>1)&3))
         uint8_t* srow = stg + r * (CW * 2);
-        if (res_co) {
 #pragma unroll
-          for (int k = 0; k < VPR; ++k) {
-            const int rr = q * 32 + (lane / VPR) + k * (32 / VPR);
-            const int cc = lane % VPR;
-            const int sw = (CW == 64) ? (cc ^ (rr & 7)) : (cc ^ ((rr >> 1) & 3));
-            *reinterpret_cast<uint4*>(stg + rr * (CW * 2) + (sw << 4)) = rres[k];
-          }
-          __syncwarp();
-#pragma unroll
-          for (int cc = 0; cc < VPR; ++cc) {
-            const int sw = (CW == 64) ? (cc ^ (r & 7)) : (cc ^ ((r >> 1) & 3));
-            const uint4 u = *reinterpret_cast<const uint4*>(srow + (sw << 4));
+        for (int cc = 0; cc < VPR; ++cc) {
+          const int sw = (CW == 64) ? (cc ^ (r & 7)) : (cc ^ ((r >> 1) & 3));
+          uint4* slot = reinterpret_cast<uint4*>(srow + (sw << 4));
+          if (has_res) {
+            const uint4 u = *slot;
             const __half2* hh = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
@@ -543,23 +554,29 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
               v[cc * 8 + 2 * t + 1] += f.y;
             }
           }
-        }
-#pragma unroll
-        for (int cc = 0; cc < VPR; ++cc) {
           uint32_t pk[4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
             __half2 hh = __floats2half2_rn(v[cc * 8 + 2 * t], v[cc * 8 + 2 * t + 1]);
             pk[t] = *reinterpret_cast<uint32_t*>(&hh);
           }
-          // CW=64: 128-byte rows, SWIZZLE_128B (chunk ^ (row & 7)); CW=32: 64-byte rows, SWIZZLE_64B (chunk ^ ((row>>1)&3))
-          const int sw = (CW == 64) ? (cc ^ (r & 7)) : (cc ^ ((r >> 1) & 3));
-          *reinterpret_cast<uint4*>(srow + (sw << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *slot = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
+        if constexpr (!TILEWIDE) {
+          fence_proxy_async_smem();
+          named_bar_sync(1 + g, 128);
+          if (issuer) {
+            tma_store_4d(&tmD, stg, ocol0, w0, h0, n0);
+            bulk_commit_group();
+          }
+        }
+      }
+      if constexpr (TILEWIDE) {
         fence_proxy_async_smem();
         named_bar_sync(1 + g, 128);
         if (issuer) {
-          tma_store_4d(&tmD, stg, ocol0, w0, h0, n0);
+          for (int chunk = g; chunk < NCHUNK; chunk += 2)
+            tma_store_4d(&tmD, staging + chunk * kChunkBytes, ntile * OUT_W + chunk * CW, w0, h0, n0);
           bulk_commit_group();
         }
       }
@@ -624,20 +641,22 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, int STAGES, int CW, bool GEGLU>
+template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE>
 static int launch_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
-                             const GemmKParams& kp, int m_tiles, int n_tiles, cudaStream_t stream) {
-  constexpr int smem = persist_smem_bytes<BN, STAGES, CW>();
+                             const CUtensorMap& tmR, const GemmKParams& kp, int m_tiles, int n_tiles,
+                             cudaStream_t stream) {
+  constexpr int smem = persist_smem_bytes<BN, STAGES, CW, GEGLU, TILEWIDE>();
+  static_assert(smem <= 227 * 1024, "persistent GEMM configuration exceeds shared memory");
   static bool configured = false;
   if (!configured) {
-    IVV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel<BN, STAGES, CW, GEGLU>,
+    IVV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel<BN, STAGES, CW, GEGLU, TILEWIDE>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   const int total = m_tiles * n_tiles;
   const int grid = total < sm_count() ? total : sm_count();
-  gemm_tc_persistent_kernel<BN, STAGES, CW, GEGLU><<<grid, kPersistThreads, smem, stream>>>(tmA, tmB, tmD, kp, n_tiles,
-                                                                                          total);
+  gemm_tc_persistent_kernel<BN, STAGES, CW, GEGLU, TILEWIDE>
+      <<<grid, kPersistThreads, smem, stream>>>(tmA, tmB, tmD, tmR, kp, n_tiles, total);
   IVV_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -744,23 +763,40 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
     if (int rc = make_tmap_f16(&tmB, a->wgt, 3, dims, strides, box, 128)) return rc;
   }
 
+  const bool res_ok = a->residual == nullptr ||
+                      ((a->res_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0);
   const bool persistent = !a->out_f32 && (a->d_ld % 8) == 0 && ((reinterpret_cast<uintptr_t>(a->d) & 15) == 0) &&
-                          (long long)m_tiles * n_tiles < (1LL << 30);
+                          res_ok && (long long)m_tiles * n_tiles < (1LL << 30);
   if (persistent) {
     const int cw = a->geglu ? 32 : (bn_sel == 256 || bn_sel == 128) ? 64 : 32;
-    CUtensorMap tmD;
-    const uint64_t dims[4] = {(uint64_t)kp.out_cols, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n_img};
-    const uint64_t strides[4] = {2, (uint64_t)a->d_ld * 2, (uint64_t)a->d_ld * 2 * a->w,
-                                 (uint64_t)a->d_ld * 2 * a->w * a->h};
+    CUtensorMap tmD, tmR;
     const uint32_t box[4] = {(uint32_t)cw, (uint32_t)kp.bw, (uint32_t)kp.bh, (uint32_t)kp.bn};
-    if (int rc = make_tmap_f16(&tmD, a->d, 4, dims, strides, box, cw == 64 ? 128 : 64)) return rc;
-    if (a->geglu) return launch_persistent<256, 4, 32, true>(tmA, tmB, tmD, kp, m_tiles, n_tiles, stream);
+    {
+      const uint64_t dims[4] = {(uint64_t)kp.out_cols, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n_img};
+      const uint64_t strides[4] = {2, (uint64_t)a->d_ld * 2, (uint64_t)a->d_ld * 2 * a->w,
+                                   (uint64_t)a->d_ld * 2 * a->w * a->h};
+      if (int rc = make_tmap_f16(&tmD, a->d, 4, dims, strides, box, cw == 64 ? 128 : 64)) return rc;
+    }
+    if (a->residual) {
+      const uint64_t dims[4] = {(uint64_t)kp.out_cols, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n_img};
+      const uint64_t strides[4] = {2, (uint64_t)a->res_ld * 2, (uint64_t)a->res_ld * 2 * a->w,
+                                   (uint64_t)a->res_ld * 2 * a->w * a->h};
+      if (int rc = make_tmap_f16(&tmR, a->residual, 4, dims, strides, box, cw == 64 ? 128 : 64)) return rc;
+    } else {
+      tmR = tmD;
+    }
+    const long long k_total = (long long)a->c * a->taps;
+    if (a->geglu) return launch_persistent<256, 4, 32, true, true>(tmA, tmB, tmD, tmR, kp, m_tiles, n_tiles, stream);
     switch (bn_sel) {
-      case 256: return launch_persistent<256, 4, 64, false>(tmA, tmB, tmD, kp, m_tiles, n_tiles, stream);
-      case 160: return launch_persistent<160, 5, 32, false>(tmA, tmB, tmD, kp, m_tiles, n_tiles, stream);
-      case 128: return launch_persistent<128, 6, 64, false>(tmA, tmB, tmD, kp, m_tiles, n_tiles, stream);
-      case 64: return launch_persistent<64, 6, 32, false>(tmA, tmB, tmD, kp, m_tiles, n_tiles, stream);
-      default: return launch_persistent<32, 6, 32, false>(tmA, tmB, tmD, kp, m_tiles, n_tiles, stream);
+      case 256:
+        // long main loops hide the epilogue: spend the shared memory on a 4th pipeline stage instead of a tile-wide slab
+        if (k_total >= 2560)
+          return launch_persistent<256, 4, 64, false, false>(tmA, tmB, tmD, tmR, kp, m_tiles, n_tiles, stream);
+        return launch_persistent<256, 3, 64, false, true>(tmA, tmB, tmD, tmR, kp, m_tiles, n_tiles, stream);
+      case 160: return launch_persistent<160, 5, 32, false, true>(tmA, tmB, tmD, tmR, kp, m_tiles, n_tiles, stream);
+      case 128: return launch_persistent<128, 6, 64, false, true>(tmA, tmB, tmD, tmR, kp, m_tiles, n_tiles, stream);
+      case 64: return launch_persistent<64, 6, 32, false, true>(tmA, tmB, tmD, tmR, kp, m_tiles, n_tiles, stream);
+      default: return launch_persistent<32, 6, 32, false, true>(tmA, tmB, tmD, tmR, kp, m_tiles, n_tiles, stream);
     }
   }
   switch (bn_sel) {

@@ -169,22 +169,25 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict
 // ------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, row held in registers (two-pass variance), optional + pe[frame]
 // ------------------------------------------------------------------------------------------------
-template <int MAXV>
+template <int LPR, int MAXV>
 __global__ void layernorm_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                  const __half* __restrict__ gamma, const __half* __restrict__ beta, long long rows,
                                  int C, float eps, const float* __restrict__ pe, long long rows_per_frame,
                                  long long frames, long long pe_start) {
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  // LPR lanes cooperate on one row (32/LPR rows per warp): short rows (C = 320) keep every lane busy
+  constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;
+  const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const bool active = row < rows;
   const int V = C / 8;
   float v[MAXV][8];
   float sum = 0.f;
-  const __half* xr = x + row * C;
+  const __half* xr = x + (active ? row : 0) * C;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    const int vec = lane + i * 32;
-    if (vec < V) {
+    const int vec = sub + i * LPR;
+    if (vec < V && active) {
       const uint4 u = *reinterpret_cast<const uint4*>(xr + vec * 8);
       const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
@@ -196,20 +199,25 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, __half* __restric
       }
     }
   }
-  const float mean = warp_sum(sum) / (float)C;
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)C;
   float sq = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    const int vec = lane + i * 32;
-    if (vec < V) {
+    const int vec = sub + i * LPR;
+    if (vec < V && active) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float d = v[i][j] - mean;
-        sq += d * d;
+        sq = fmaf(d, d, sq);
       }
     }
   }
-  const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  if (!active) return;
+  const float rstd = rsqrtf(sq / (float)C + eps);
   const float* per = nullptr;
   if (pe) {
     const long long frame = (row / rows_per_frame) % frames;
@@ -218,24 +226,29 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, __half* __restric
   __half* yr = y + row * C;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    const int vec = lane + i * 32;
+    const int vec = sub + i * LPR;
     if (vec < V) {
       const uint4 ug = *reinterpret_cast<const uint4*>(gamma + vec * 8);
       const uint4 ub = *reinterpret_cast<const uint4*>(beta + vec * 8);
       const __half2* hg = reinterpret_cast<const __half2*>(&ug);
       const __half2* hb = reinterpret_cast<const __half2*>(&ub);
+      float pv[8];
+      if (per) {
+        const float4 p0 = *reinterpret_cast<const float4*>(per + vec * 8);
+        const float4 p1 = *reinterpret_cast<const float4*>(per + vec * 8 + 4);
+        pv[0] = p0.x, pv[1] = p0.y, pv[2] = p0.z, pv[3] = p0.w, pv[4] = p1.x, pv[5] = p1.y, pv[6] = p1.z, pv[7] = p1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pv[j] = 0.f;
+      }
       uint4 o;
       __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 g = __half22float2(hg[j]);
         const float2 b = __half22float2(hb[j]);
-        float o0 = (v[i][2 * j] - mean) * rstd * g.x + b.x;
-        float o1 = (v[i][2 * j + 1] - mean) * rstd * g.y + b.y;
-        if (per) {
-          o0 += per[vec * 8 + 2 * j];
-          o1 += per[vec * 8 + 2 * j + 1];
-        }
+        const float o0 = fmaf((v[i][2 * j] - mean) * rstd, g.x, b.x) + pv[2 * j];
+        const float o1 = fmaf((v[i][2 * j + 1] - mean) * rstd, g.y, b.y) + pv[2 * j + 1];
         oh[j] = __floats2half2_rn(o0, o1);
       }
       *reinterpret_cast<uint4*>(yr + vec * 8) = o;
@@ -355,20 +368,24 @@ extern "C" int ivv_layernorm(const void* x, void* y, const void* gamma, const vo
               (long long)c);
   IVV_REQUIRE(!pe || (rows_per_frame > 0 && frames > 0), "ivv_layernorm: pe given without frame geometry");
   const int warps = 8;
-  const long long blocks = (rows + warps - 1) / warps;
   const __half* xx = reinterpret_cast<const __half*>(x);
   __half* yy = reinterpret_cast<__half*>(y);
   const __half* g = reinterpret_cast<const __half*>(gamma);
   const __half* b = reinterpret_cast<const __half*>(beta);
-  if (c <= 256 * 2)
-    layernorm_kernel<2><<<(unsigned)blocks, warps * 32, 0, stream>>>(xx, yy, g, b, rows, (int)c, eps, pe,
-                                                                     rows_per_frame, frames, pe_start);
-  else if (c <= 256 * 5)
-    layernorm_kernel<5><<<(unsigned)blocks, warps * 32, 0, stream>>>(xx, yy, g, b, rows, (int)c, eps, pe,
-                                                                     rows_per_frame, frames, pe_start);
-  else
-    layernorm_kernel<8><<<(unsigned)blocks, warps * 32, 0, stream>>>(xx, yy, g, b, rows, (int)c, eps, pe,
-                                                                     rows_per_frame, frames, pe_start);
+  IVV_REQUIRE(!pe || (reinterpret_cast<uintptr_t>(pe) & 15) == 0, "ivv_layernorm: pe must be 16-byte aligned");
+  const int V = (int)(c / 8);
+#define IVV_LN_LAUNCH(LPR, MAXV)                                                                                   \
+  {                                                                                                                \
+    const long long rows_per_block = (long long)warps * (32 / LPR);                                                \
+    const long long blocks = (rows + rows_per_block - 1) / rows_per_block;                                         \
+    layernorm_kernel<LPR, MAXV><<<(unsigned)blocks, warps * 32, 0, stream>>>(xx, yy, g, b, rows, (int)c, eps, pe,  \
+                                                                             rows_per_frame, frames, pe_start);   \
+  }
+  if (V <= 8 * 5) IVV_LN_LAUNCH(8, 5)
+  else if (V <= 16 * 5) IVV_LN_LAUNCH(16, 5)
+  else if (V <= 32 * 5) IVV_LN_LAUNCH(32, 5)
+  else IVV_LN_LAUNCH(32, 8)
+#undef IVV_LN_LAUNCH
   IVV_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
