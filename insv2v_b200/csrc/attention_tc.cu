@@ -7,7 +7,7 @@
 // rescale of the TMEM-resident O), warp 4: TMA producer, warp 5: MMA issuer + TMEM owner.
 // Per 128-key block:  S = Q K^T (TMEM cols [0,128))  ->  P = exp2(S*sl - m*sl) as fp16 in swizzled smem
 //                     ->  O += P V (TMEM cols [128, 128+dn)).
-// TMEM use is 256 columns for d <= 128 so two CTAs share an SM and one CTA's softmax overlaps the other's MMAs.
+// TMEM use is 256 columns for d <= 111 so two CTAs share an SM and one CTA's softmax overlaps the other's MMAs.
 #include "../../include/ivv.h"
 #include "common.cuh"
 
@@ -33,6 +33,15 @@ constexpr int attn_smem_bytes() {
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// two exp2 per MUFU op: pack (lo, hi) to f16x2 (round to nearest) and exponentiate in half precision — P is consumed
+// as fp16 by the tensor core anyway, and the arguments are <= 0 so the absolute error of the fp16 argument is tiny
+// exactly where P is large
+__device__ __forceinline__ uint32_t ex2_h2(float lo, float hi) {
+  uint32_t packed, y;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(packed) : "f"(hi), "f"(lo));
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(packed));
   return y;
 }
 
@@ -62,8 +71,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int nb = blockIdx.z;
   const int nkb = nb / p.kv_div;
   const int nblk = (p.s_kv + kKV - 1) / kKV;
-  const int dk16 = (p.d + 15) / 16;  // K-steps of QK^T; also dn = dk16*16 is the N of PV
-  const int dn = dk16 * 16;
+  const int dk16 = (p.d + 15) / 16;         // K-steps of S = Q K^T
+  const int dn = (p.d + 1 + 15) / 16 * 16;  // N of O = P [V | 1]: d value columns + the ones column at index d
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmQ);
@@ -110,7 +119,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   } else if (warp == 5) {
     if (lane == 0) {
       // ===== MMA issuer =====
-      const uint32_t idesc_pv = umma_idesc_f16(128, dn, 0, 1);  // B (=V) is MN-major
+      const uint32_t idesc_pv = umma_idesc_f16(128, dn, 0, 1);  // B (= [V | 1]) is MN-major
       mbar_wait(q_full, 0);
       int st = 0;
       uint32_t ph = 0;
@@ -150,30 +159,51 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int r = warp * 32 + lane;
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
     const float sl = p.scale_log2;
-    float m_run = -INFINITY, l_run = 0.f;
+    float m_run = -INFINITY;
+    // The softmax denominator is never summed on the CUDA cores: a column of ones is written into the V tile at
+    // column d (slab d/64, 16-byte chunk (d%64)/8, element d%8), so O[:, d] accumulates sum(P) in fp32 inside the
+    // tensor core and follows every online rescale for free.
+    const int one_slab = p.d >> 6, one_chunk = (p.d & 63) >> 3, one_elem = p.d & 7;
+    int st = 0;
     for (int j = 0; j < nblk; ++j) {
       const int valid = min(kKV, p.s_kv - j * kKV);
       const int nchunk = (valid + 31) / 32;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: row max
+      // pass 1: row max (full blocks take the mask-free path: the softmax warps are instruction-issue bound)
       float mx = -INFINITY;
-      for (int c = 0; c < nchunk; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, v);
-        tmem_ld_wait();
+      if (valid == kKV) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_S + lane_off + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      } else {
+        for (int c = 0; c < nchunk; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_S + lane_off + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
       }
-      const float m_new = fmaxf(m_run, mx);
+      // Lazy rescale: keep the running reference m_run while the new block maximum exceeds it by less than a factor
+      // 2^2 (exp2 arguments stay below 2, where the fp16 argument grid is still 2^-10: P keeps ~fp16 accuracy; O and
+      // the denominator column accumulate in fp32). O is then rescaled only when a row's maximum jumps, which after the
+      // first blocks is rare, instead of on every block.
+      float m_new = m_run;
+      if ((mx - m_run) * sl > 2.f) m_new = mx;  // also taken on the first block (m_run = -inf)
       const float alpha = ex2((m_run - m_new) * sl);
       const float m_sl = m_new * sl;
       if (j > 0) {
         // previous P V must have retired before O is rescaled and P is overwritten
         mbar_wait(pv_done, (j - 1) & 1);
         tc_fence_after();
-        if (!__all_sync(0xffffffffu, alpha == 1.f)) {
+        if (!__all_sync(0xffffffffu, m_new == m_run)) {
           for (int c = 0; c < dn; c += 16) {
             uint32_t o[16];
             tmem_ld16(tmem_O + lane_off + c, o);
@@ -185,31 +215,52 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tmem_st_wait();
         }
       }
-      // pass 2: P = exp2(S*sl - m*sl) -> fp16, K-major SW128 smem (row r, 16-byte chunk cc ^ (r & 7))
-      float rowsum = 0.f;
-      for (int c = 0; c < nchunk; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_S + lane_off + c * 32, v);
-        tmem_ld_wait();
-        uint8_t* slab = sP + (c >> 1) * kSlab + r * 128;
+      // pass 2: P = exp2(S*sl - m*sl) -> fp16 pairs, K-major SW128 smem (row r, 16-byte chunk cc ^ (r & 7))
+      if (valid == kKV) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint32_t pk[4];
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_S + lane_off + c * 32, v);
+          tmem_ld_wait();
+          uint8_t* slab = sP + (c >> 1) * kSlab + r * 128;
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int i0 = g * 8 + 2 * t;
-            float p0 = (c * 32 + i0 < valid) ? ex2(__uint_as_float(v[i0]) * sl - m_sl) : 0.f;
-            float p1 = (c * 32 + i0 + 1 < valid) ? ex2(__uint_as_float(v[i0 + 1]) * sl - m_sl) : 0.f;
-            rowsum += p0 + p1;
-            __half2 h = __floats2half2_rn(p0, p1);
-            pk[t] = *reinterpret_cast<uint32_t*>(&h);
+          for (int g = 0; g < 4; ++g) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+              pk[t] = ex2_h2(fmaf(__uint_as_float(v[g * 8 + 2 * t]), sl, -m_sl),
+                             fmaf(__uint_as_float(v[g * 8 + 2 * t + 1]), sl, -m_sl));
+            const int cc = (c & 1) * 4 + g;
+            *reinterpret_cast<uint4*>(slab + ((cc ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
-          const int cc = (c & 1) * 4 + g;  // 16-byte chunk index inside the 128-byte row
-          *reinterpret_cast<uint4*>(slab + ((cc ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      } else {
+        for (int c = 0; c < nchunk; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_S + lane_off + c * 32, v);
+          tmem_ld_wait();
+          uint8_t* slab = sP + (c >> 1) * kSlab + r * 128;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const int i0 = g * 8 + 2 * t;
+              const float x0 = (c * 32 + i0 < valid) ? fmaf(__uint_as_float(v[i0]), sl, -m_sl) : -INFINITY;
+              const float x1 = (c * 32 + i0 + 1 < valid) ? fmaf(__uint_as_float(v[i0 + 1]), sl, -m_sl) : -INFINITY;
+              pk[t] = ex2_h2(x0, x1);
+            }
+            const int cc = (c & 1) * 4 + g;  // 16-byte chunk index inside the 128-byte row
+            *reinterpret_cast<uint4*>(slab + ((cc ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
         }
       }
-      l_run = l_run * alpha + rowsum;
       m_run = m_new;
+      {  // ones column of this V stage, key row r
+        uint8_t* vrow = sV + (st * DC + one_slab) * kSlab + r * 128;
+        *reinterpret_cast<__half*>(vrow + ((one_chunk ^ (r & 7)) << 4) + one_elem * 2) = __float2half_rn(1.f);
+      }
+      if (++st == NS) st = 0;
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive(p_full);
@@ -217,11 +268,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // ---- epilogue: O / l -> global ----
     mbar_wait(pv_done, (nblk - 1) & 1);
     tc_fence_after();
-    const float inv_l = 1.f / l_run;
+    float inv_l;
+    {
+      uint32_t o[16];
+      tmem_ld16(tmem_O + lane_off + (p.d & ~15), o);
+      tmem_ld_wait();
+      float l = 1.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i == (p.d & 15)) l = __uint_as_float(o[i]);
+      inv_l = 1.f / l;
+    }
     const int row = q0 + r;
     __half* orow = p.o + (static_cast<long long>(nb) * p.s_q + row) * p.o_ld + static_cast<long long>(head) * p.d;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(orow) & 15) == 0);
-    for (int c = 0; c < dn; c += 16) {
+    for (int c = 0; c < p.d; c += 16) {
       uint32_t o[16];
       tmem_ld16(tmem_O + lane_off + c, o);
       tmem_ld_wait();
@@ -282,7 +343,7 @@ extern "C" int ivv_attention(const void* q, int64_t q_ld, const void* k, const v
   IVV_REQUIRE(n_batch > 0 && s_q > 0 && s_kv > 0 && heads > 0 && kv_div > 0, "ivv_attention: empty problem");
   IVV_REQUIRE(n_batch % kv_div == 0, "ivv_attention: n_batch (%lld) not a multiple of kv_div (%lld)",
               (long long)n_batch, (long long)kv_div);
-  IVV_REQUIRE(d % 8 == 0 && d >= 8 && d <= 192, "ivv_attention: head dim %d must be a multiple of 8 in [8, 192]", d);
+  IVV_REQUIRE(d % 8 == 0 && d >= 8 && d <= 184, "ivv_attention: head dim %d must be a multiple of 8 in [8, 184]", d);
   IVV_REQUIRE(q_ld % 8 == 0 && kv_ld % 8 == 0 && o_ld % 8 == 0, "ivv_attention: leading dims must be multiples of 8");
   IVV_REQUIRE(n_batch <= 65535 && heads <= 65535, "ivv_attention: grid too large");
 
@@ -309,7 +370,7 @@ extern "C" int ivv_attention(const void* q, int64_t q_ld, const void* k, const v
     if (int rc = make_tmap_f16(&tv, v, 4, dims, str, box, 128)) return rc;
   }
   dim3 grid((unsigned)((s_q + kQ - 1) / kQ), (unsigned)heads, (unsigned)n_batch);
-  const int dc = (d + 63) / 64;
+  const int dc = (d + 1 + 63) / 64;  // 64-wide chunks holding the d value columns plus the ones column
   if (dc == 1) return launch_attn<1, 2>(tq, tk, tv, ap, grid, stream);
   if (dc == 2) return launch_attn<2, 2>(tq, tk, tv, ap, grid, stream);
   return launch_attn<3, 1>(tq, tk, tv, ap, grid, stream);
