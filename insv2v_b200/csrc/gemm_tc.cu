@@ -8,6 +8,8 @@
 // no im2col buffer ever exists. A Linear layer is the same kernel with taps = 1 and box (128, 1, 1).
 // Warp roles: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (+TMEM owner), warps 2..5 = epilogue
 // (tcgen05.ld -> bias / temb row-bias / residual / GEGLU -> global).  Reference call sites: ivv.h (K1/K2/K11).
+#include <cstdlib>
+
 #include "../../include/ivv.h"
 #include "common.cuh"
 
@@ -108,7 +110,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tw = mtile % p.tiles_w;
   const int th = (mtile / p.tiles_w) % p.tiles_h;
   const int tg = mtile / (p.tiles_w * p.tiles_h);
-  const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tg * p.bn;
+  const int w0 = tw * p.bw, h0 = th * p.bh;
+      const int n0 = mtile < p.tiles_w * p.tiles_h * p.tiles_g ? tg * p.bn : p.NI;  // ghost tile of an odd cluster: fully out of bounds
   const int total_it = p.taps * p.kblocks;
 
   if (threadIdx.x == 0) {
@@ -293,14 +296,21 @@ constexpr int persist_smem_bytes() {
   return STAGES * (kABytes + BN * 128) + (TILEWIDE ? kBlockM * (GEGLU ? BN / 2 : BN) * 2 : 2 * kBlockM * CW * 2) + 256;
 }
 
-template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE>
+template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, int CS>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                           const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
                           const __grid_constant__ GemmKParams p, int n_tiles, int total_tiles) {
+  // CS > 1: a cluster of CS CTAs works on CS consecutive M tiles of the same N tile; every CTA fetches 1/CS of the
+  // weight tile and TMA-multicasts it to all of them, cutting the L2->SM operand traffic (the measured bound of the
+  // K <= 1280 GEMMs). total_tiles then counts super tiles (M-tile groups x N tiles) and the loop strides by clusters.
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   constexpr int kStageBytes = kABytes + BN * 128;
+  constexpr uint16_t kMask = (1u << CS) - 1;
+  const int crank = CS > 1 ? (int)cluster_ctarank() : 0;
+  const int tile_first = CS > 1 ? (int)cluster_id_x() : (int)blockIdx.x;
+  const int tile_step = CS > 1 ? (int)num_clusters_x() : (int)gridDim.x;
   constexpr int kChunkBytes = kBlockM * CW * 2;  // one [128 rows x CW fp16] swizzled slab per column chunk
   constexpr int kStagingBytes = TILEWIDE ? kBlockM * (GEGLU ? BN / 2 : BN) * 2 : 2 * kChunkBytes;
   constexpr uint32_t kAccStride = acc_stride_for<BN>();
@@ -324,7 +334,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     tma_prefetch_desc(&tmR);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CS);  // every CTA of the cluster must have consumed the stage
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
@@ -335,7 +345,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   }
   if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr);
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CS > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -344,13 +354,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       // ===== TMA producer =====
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
         const int ntile = tile % n_tiles;
-        const int mtile = tile / n_tiles;
+        const int mtile = (tile / n_tiles) * CS + crank;
         const int tw = mtile % p.tiles_w;
         const int th = (mtile / p.tiles_w) % p.tiles_h;
         const int tg = mtile / (p.tiles_w * p.tiles_h);
-        const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tg * p.bn;
+        const int w0 = tw * p.bw, h0 = th * p.bh;
+      const int n0 = mtile < p.tiles_w * p.tiles_h * p.tiles_g ? tg * p.bn : p.NI;  // ghost tile of an odd cluster: fully out of bounds
         for (int it = 0; it < its_per_tile; ++it) {
           const int tap = it / p.kblocks;
           const int kb = it - tap * p.kblocks;
@@ -363,7 +374,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           uint8_t* sa = smem + stage * kStageBytes;
           mbar_expect_tx(&full_bar[stage], kStageBytes);
           tma_load_4d(sa, &tmA, &full_bar[stage], kb * kBlockK, w0 + dx, h0 + dy, n0);
-          tma_load_3d(sa + kABytes, &tmB, &full_bar[stage], kb * kBlockK, ntile * BN, tap);
+          if constexpr (CS > 1)
+            tma_load_3d_multicast(sa + kABytes + crank * (BN / CS) * 128, &tmB, &full_bar[stage], kb * kBlockK,
+                                  ntile * BN + crank * (BN / CS), tap, kMask);
+          else
+            tma_load_3d(sa + kABytes, &tmB, &full_bar[stage], kb * kBlockK, ntile * BN, tap);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -378,7 +393,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++local) {
         const int buf = local & 1;
         mbar_wait(&tmem_empty_bar[buf], ((local >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
@@ -392,7 +407,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
             umma_f16_ss(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
+          if constexpr (CS > 1) umma_commit_multicast(&empty_bar[stage], kMask); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -417,13 +432,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     const int my_chunks = (NCHUNK - g + 1) / 2;  // chunks g, g+2, ...
     uint32_t res_phase = 0;
     int local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++local) {
       const int ntile = tile % n_tiles;
-      const int mtile = tile / n_tiles;
+      const int mtile = (tile / n_tiles) * CS + crank;
       const int tw = mtile % p.tiles_w;
       const int th = (mtile / p.tiles_w) % p.tiles_h;
       const int tg = mtile / (p.tiles_w * p.tiles_h);
-      const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tg * p.bn;
+      const int w0 = tw * p.bw, h0 = th * p.bh;
+      const int n0 = mtile < p.tiles_w * p.tiles_h * p.tiles_g ? tg * p.bn : p.NI;  // ghost tile of an odd cluster: fully out of bounds
       const int w = w0 + wi, h = h0 + hi, n = n0 + ni;
       const bool valid = (w < p.W) && (h < p.H) && (n < p.NI);
       const long long pix = (static_cast<long long>(n) * p.H + h) * p.W + w;
@@ -589,7 +605,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   }
 
   tc_fence_before();
-  __syncthreads();
+  // no CTA may exit while a peer can still multicast into its shared memory or signal its barriers
+  if constexpr (CS > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
@@ -641,24 +658,46 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE>
-static int launch_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
-                             const CUtensorMap& tmR, const GemmKParams& kp, int m_tiles, int n_tiles,
-                             cudaStream_t stream) {
+template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, int CS>
+static int launch_persistent_cs(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
+                                const CUtensorMap& tmR, const GemmKParams& kp, int m_tiles, int n_tiles,
+                                cudaStream_t stream) {
   constexpr int smem = persist_smem_bytes<BN, STAGES, CW, GEGLU, TILEWIDE>();
   static_assert(smem <= 227 * 1024, "persistent GEMM configuration exceeds shared memory");
+  auto kern = gemm_tc_persistent_kernel<BN, STAGES, CW, GEGLU, TILEWIDE, CS>;
   static bool configured = false;
   if (!configured) {
-    IVV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_persistent_kernel<BN, STAGES, CW, GEGLU, TILEWIDE>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    IVV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  const int total = m_tiles * n_tiles;
-  const int grid = total < sm_count() ? total : sm_count();
-  gemm_tc_persistent_kernel<BN, STAGES, CW, GEGLU, TILEWIDE>
-      <<<grid, kPersistThreads, smem, stream>>>(tmA, tmB, tmD, tmR, kp, n_tiles, total);
-  IVV_CHECK_CUDA(cudaGetLastError());
+  const int groups = (m_tiles + CS - 1) / CS;
+  const int total = groups * n_tiles;  // (super) tiles
+  int clusters = sm_count() / CS;
+  if (clusters > total) clusters = total;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(clusters * CS));
+  cfg.blockDim = dim3(kPersistThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CS > 1 ? 1 : 0;
+  IVV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, tmR, kp, n_tiles, total));
   return 0;
+}
+
+// cluster size 2 (weight tile multicast) whenever the M tiles pair up; IVV_CLUSTER=1 disables it (tuning hook)
+template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE>
+static int launch_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB2, const CUtensorMap& tmB1,
+                             const CUtensorMap& tmD, const CUtensorMap& tmR, const GemmKParams& kp, int m_tiles,
+                             int n_tiles, int cs, cudaStream_t stream) {
+  if (cs == 2)
+    return launch_persistent_cs<BN, STAGES, CW, GEGLU, TILEWIDE, 2>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
+  return launch_persistent_cs<BN, STAGES, CW, GEGLU, TILEWIDE, 1>(tmA, tmB1, tmD, tmR, kp, m_tiles, n_tiles, stream);
 }
 
 template <int BN, int STAGES>
@@ -722,33 +761,34 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
   if (a->geglu) {
     bn_sel = 256;
   } else {
+    // Tile-width choice from a measured cost model (tools/tile_sweep.py): these GEMMs are bound by operand delivery
+    // from L2 (~12 TB/s), so time ~ padding x bytes fetched per output (1/BN + 1/128) / wave efficiency on 148 SMs.
     const int cands[5] = {256, 160, 128, 64, 32};
-    double best_waste = 1e9;
+    double best = 1e30;
+    bn_sel = 128;
     for (int i = 0; i < 5; ++i) {
-      const int tiles = (int)((a->n_out + cands[i] - 1) / cands[i]);
-      best_waste = std::min(best_waste, (double)tiles * cands[i] / (double)a->n_out);
-    }
-    bn_sel = -1;
-    int fallback = -1;
-    long long fallback_ctas = -1;
-    for (int i = 0; i < 5; ++i) {
-      const int tiles = (int)((a->n_out + cands[i] - 1) / cands[i]);
-      const double waste = (double)tiles * cands[i] / (double)a->n_out;
-      if (waste > best_waste * 1.07) continue;
-      const long long ctas = (long long)tiles * m_tiles;
-      if (ctas >= 148 && bn_sel < 0) bn_sel = cands[i];
-      if (ctas > fallback_ctas && cands[i] >= 64) {
-        fallback_ctas = ctas;
-        fallback = cands[i];
+      const long long nt = (a->n_out + cands[i] - 1) / cands[i];
+      const double waste = (double)nt * cands[i] / (double)a->n_out;
+      const long long tiles = nt * m_tiles;
+      const long long waves = (tiles + sm_count() - 1) / sm_count();
+      const double eff = (double)tiles / (double)(waves * sm_count());
+      const double cost = waste * (1.0 / cands[i] + 1.0 / 128.0) / eff;
+      if (cost < best * 0.999) {
+        best = cost;
+        bn_sel = cands[i];
       }
-      if (fallback < 0) fallback = cands[i];
     }
-    if (bn_sel < 0) bn_sel = fallback;
+  }
+  if (!a->geglu) {  // tuning hook (tools/tile_sweep.py): IVV_FORCE_BN=32|64|128|160|256
+    if (const char* f = getenv("IVV_FORCE_BN")) {
+      const int v = atoi(f);
+      if (v == 32 || v == 64 || v == 128 || v == 160 || v == 256) bn_sel = v;
+    }
   }
   const int n_tiles = (int)((a->n_out + bn_sel - 1) / bn_sel);
 
   // ---- tensor maps ----
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmB2;
   {
     const uint64_t dims[4] = {(uint64_t)a->c, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n_img};
     const uint64_t strides[4] = {2, (uint64_t)a->a_ld * 2, (uint64_t)a->a_ld * 2 * a->w,
@@ -761,6 +801,8 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
     const uint64_t strides[3] = {2, (uint64_t)a->w_ld * 2, (uint64_t)a->w_ld * 2 * a->n_out};
     const uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)bn_sel, 1};
     if (int rc = make_tmap_f16(&tmB, a->wgt, 3, dims, strides, box, 128)) return rc;
+    const uint32_t box2[3] = {(uint32_t)kBlockK, (uint32_t)(bn_sel / 2), 1};  // half tile per CTA of a 2-CTA cluster
+    if (int rc = make_tmap_f16(&tmB2, a->wgt, 3, dims, strides, box2, 128)) return rc;
   }
 
   const bool res_ok = a->residual == nullptr ||
@@ -786,17 +828,20 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
       tmR = tmD;
     }
     const long long k_total = (long long)a->c * a->taps;
-    if (a->geglu) return launch_persistent<256, 4, 32, true, true>(tmA, tmB, tmD, tmR, kp, m_tiles, n_tiles, stream);
+    // pairs of M tiles share the weight tile through TMA multicast when there is enough work to pair up
+    int cs = (m_tiles >= 2 && (long long)m_tiles * n_tiles >= sm_count()) ? 2 : 1;
+    if (const char* f = getenv("IVV_CLUSTER")) cs = atoi(f) == 2 ? (m_tiles >= 2 ? 2 : 1) : 1;
+    if (a->geglu) return launch_persistent<256, 4, 32, true, true>(tmA, tmB2, tmB, tmD, tmR, kp, m_tiles, n_tiles, cs, stream);
     switch (bn_sel) {
       case 256:
         // long main loops hide the epilogue: spend the shared memory on a 4th pipeline stage instead of a tile-wide slab
         if (k_total >= 2560)
-          return launch_persistent<256, 4, 64, false, false>(tmA, tmB, tmD, tmR, kp, m_tiles, n_tiles, stream);
-        return launch_persistent<256, 3, 64, false, true>(tmA, tmB, tmD, tmR, kp, m_tiles, n_tiles, stream);
-      case 160: return launch_persistent<160, 5, 32, false, true>(tmA, tmB, tmD, tmR, kp, m_tiles, n_tiles, stream);
-      case 128: return launch_persistent<128, 6, 64, false, true>(tmA, tmB, tmD, tmR, kp, m_tiles, n_tiles, stream);
-      case 64: return launch_persistent<64, 6, 32, false, true>(tmA, tmB, tmD, tmR, kp, m_tiles, n_tiles, stream);
-      default: return launch_persistent<32, 6, 32, false, true>(tmA, tmB, tmD, tmR, kp, m_tiles, n_tiles, stream);
+          return launch_persistent<256, 4, 64, false, false>(tmA, tmB2, tmB, tmD, tmR, kp, m_tiles, n_tiles, cs, stream);
+        return launch_persistent<256, 3, 64, false, true>(tmA, tmB2, tmB, tmD, tmR, kp, m_tiles, n_tiles, cs, stream);
+      case 160: return launch_persistent<160, 5, 32, false, true>(tmA, tmB2, tmB, tmD, tmR, kp, m_tiles, n_tiles, cs, stream);
+      case 128: return launch_persistent<128, 6, 64, false, true>(tmA, tmB2, tmB, tmD, tmR, kp, m_tiles, n_tiles, cs, stream);
+      case 64: return launch_persistent<64, 6, 32, false, true>(tmA, tmB2, tmB, tmD, tmR, kp, m_tiles, n_tiles, cs, stream);
+      default: return launch_persistent<32, 6, 32, false, true>(tmA, tmB2, tmB, tmD, tmR, kp, m_tiles, n_tiles, cs, stream);
     }
   }
   switch (bn_sel) {
