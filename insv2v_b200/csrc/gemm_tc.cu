@@ -828,9 +828,10 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
       tmR = tmD;
     }
     const long long k_total = (long long)a->c * a->taps;
-    // pairs of M tiles share the weight tile through TMA multicast when there is enough work to pair up
-    int cs = (m_tiles >= 2 && (long long)m_tiles * n_tiles >= sm_count()) ? 2 : 1;
-    if (const char* f = getenv("IVV_CLUSTER")) cs = atoi(f) == 2 ? (m_tiles >= 2 ? 2 : 1) : 1;
+    // 2-CTA clusters with a TMA-multicast weight tile: measured neutral (tools/profile_ops.py with IVV_CLUSTER=2) — the
+    // limit is the ~60 B/clk each SM can ingest, which multicast does not reduce — so it is opt-in.
+    int cs = 1;
+    if (const char* f = getenv("IVV_CLUSTER")) cs = (atoi(f) == 2 && m_tiles >= 2) ? 2 : 1;
     if (a->geglu) return launch_persistent<256, 4, 32, true, true>(tmA, tmB2, tmB, tmD, tmR, kp, m_tiles, n_tiles, cs, stream);
     switch (bn_sel) {
       case 256:
