@@ -290,13 +290,13 @@ template <int BN>
 constexpr uint32_t acc_stride_for() {
   return BN <= 32 ? 32u : BN <= 64 ? 64u : BN <= 128 ? 128u : 256u;
 }
-template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE>
+template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, bool TWO = false>
 constexpr int persist_smem_bytes() {
   // TILEWIDE: the whole fp16 output tile is staged; otherwise one CW-wide slab per epilogue group
-  return STAGES * (kABytes + BN * 128) + (TILEWIDE ? kBlockM * (GEGLU ? BN / 2 : BN) * 2 : 2 * kBlockM * CW * 2) + 256;
+  return STAGES * (kABytes + (TWO ? BN / 2 : BN) * 128) + (TILEWIDE ? kBlockM * (GEGLU ? BN / 2 : BN) * 2 : 2 * kBlockM * CW * 2) + 256;
 }
 
-template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, int CS>
+template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, int CS, bool TWO>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                           const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
@@ -306,7 +306,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   // K <= 1280 GEMMs). total_tiles then counts super tiles (M-tile groups x N tiles) and the loop strides by clusters.
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  constexpr int kStageBytes = kABytes + BN * 128;
+  // TWO: the pair runs ONE tcgen05.mma.cta_group::2 (M = 256): each CTA stages its own 128 A rows and only HALF of the
+  // weight tile, which is what lifts the ~60 B/clk per-SM operand-ingest limit of the single-CTA kernel.
+  static_assert(!TWO || CS == 2, "pair MMA needs a 2-CTA cluster");
+  constexpr int kBRows = TWO ? BN / 2 : BN;
+  constexpr int kStageBytes = kABytes + kBRows * 128;
   constexpr uint16_t kMask = (1u << CS) - 1;
   const int crank = CS > 1 ? (int)cluster_ctarank() : 0;
   const int tile_first = CS > 1 ? (int)cluster_id_x() : (int)blockIdx.x;
@@ -333,17 +337,19 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     tma_prefetch_desc(&tmD);
     tma_prefetch_desc(&tmR);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CS);  // every CTA of the cluster must have consumed the stage
+      mbar_init(&full_bar[s], TWO ? 2 : 1);      // pair mode: leader's expect_tx + the peer's remote arrive
+      mbar_init(&empty_bar[s], TWO ? 1 : CS);    // multicast mode: every CTA must have consumed the stage
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 8);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[b], TWO ? 16 : 8);  // one arrive per epilogue warp (of both CTAs in pair mode)
       mbar_init(&res_bar[b], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<kTmemCols>(tmem_ptr);
+  if (warp == 1) {
+    if constexpr (TWO) tmem_alloc_2sm<kTmemCols>(tmem_ptr); else tmem_alloc<kTmemCols>(tmem_ptr);
+  }
   tc_fence_before();
   if constexpr (CS > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
@@ -372,6 +378,18 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
+          if constexpr (TWO) {
+            // bytes of BOTH CTAs are counted on the leader's barrier; the peer announces itself with a remote arrive
+            const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes); else mbar_arrive_cluster(lead_bar);
+            tma_load_4d_2sm(sa, &tmA, lead_bar, kb * kBlockK, w0 + dx, h0 + dy, n0);
+            tma_load_3d_2sm(sa + kABytes, &tmB, lead_bar, kb * kBlockK, ntile * BN + crank * kBRows, tap);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           mbar_expect_tx(&full_bar[stage], kStageBytes);
           tma_load_4d(sa, &tmA, &full_bar[stage], kb * kBlockK, w0 + dx, h0 + dy, n0);
           if constexpr (CS > 1)
@@ -387,9 +405,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===== MMA issuer =====
-      constexpr uint32_t idesc = umma_idesc_f16(kBlockM, BN, 0, 0);
+    if (lane == 0 && (!TWO || crank == 0)) {
+      // ===== MMA issuer (pair mode: the leader CTA issues for both) =====
+      constexpr uint32_t idesc = umma_idesc_f16(TWO ? 2 * kBlockM : kBlockM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -405,15 +423,19 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           const uint64_t adesc = umma_desc_kmajor_sw128(sa);
           const uint64_t bdesc = umma_desc_kmajor_sw128(sa + kABytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_f16_ss(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
-          if constexpr (CS > 1) umma_commit_multicast(&empty_bar[stage], kMask); else umma_commit(&empty_bar[stage]);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            if constexpr (TWO) umma_f16_ss_2sm(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+            else umma_f16_ss(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          if constexpr (TWO) umma_commit_2sm(&empty_bar[stage], kMask);
+          else if constexpr (CS > 1) umma_commit_multicast(&empty_bar[stage], kMask);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full_bar[buf]);
+        if constexpr (TWO) umma_commit_2sm(&tmem_full_bar[buf], kMask); else umma_commit(&tmem_full_bar[buf]);
       }
     }
   } else {
@@ -428,6 +450,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     constexpr int OUT_W = GEGLU ? BN / 2 : BN;  // output columns per tile
     constexpr int NCHUNK = OUT_W / CW;
     constexpr int VPR = CW / 8;                 // 16-byte vectors per staging row
+    // accumulator hand-back: in pair mode the MMA issuer lives in the leader CTA
+    auto release_acc = [&](int buf_) {
+      if constexpr (TWO) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[buf_]), 0));
+      else mbar_arrive(&tmem_empty_bar[buf_]);
+    };
     const bool has_res = !GEGLU && p.residual != nullptr;
     const int my_chunks = (NCHUNK - g + 1) / 2;  // chunks g, g+2, ...
     uint32_t res_phase = 0;
@@ -500,7 +527,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           }
           if (chunk + 2 >= NCHUNK) {  // last chunk of this warp: the accumulator can be handed back to the MMA warp
             tc_fence_before();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+            if (lane == 0) release_acc(buf);
           }
 #pragma unroll
           for (int s = 0; s < CW; s += 8) {
@@ -550,7 +577,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           }
           if (chunk + 2 >= NCHUNK) {
             tc_fence_before();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+            if (lane == 0) release_acc(buf);
           }
         }
         // ---- own row of the slab: add the TMA-fetched residual, then overwrite it with the fp16 result ----
@@ -598,7 +625,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       }
       if (NCHUNK == 1 && g == 1) {  // this group had no chunk: still release the accumulator
         tc_fence_before();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        if (lane == 0) release_acc(buf);
       }
     }
     if (issuer) bulk_wait_group<0>();
@@ -610,7 +637,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    if constexpr (TWO) tmem_dealloc_2sm<kTmemCols>(tmem_base); else tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
@@ -658,13 +685,13 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, int CS>
+template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, int CS, bool TWO = false>
 static int launch_persistent_cs(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                                 const CUtensorMap& tmR, const GemmKParams& kp, int m_tiles, int n_tiles,
                                 cudaStream_t stream) {
-  constexpr int smem = persist_smem_bytes<BN, STAGES, CW, GEGLU, TILEWIDE>();
+  constexpr int smem = persist_smem_bytes<BN, STAGES, CW, GEGLU, TILEWIDE, TWO>();
   static_assert(smem <= 227 * 1024, "persistent GEMM configuration exceeds shared memory");
-  auto kern = gemm_tc_persistent_kernel<BN, STAGES, CW, GEGLU, TILEWIDE, CS>;
+  auto kern = gemm_tc_persistent_kernel<BN, STAGES, CW, GEGLU, TILEWIDE, CS, TWO>;
   static bool configured = false;
   if (!configured) {
     IVV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -772,7 +799,7 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
       const long long tiles = nt * m_tiles;
       const long long waves = (tiles + sm_count() - 1) / sm_count();
       const double eff = (double)tiles / (double)(waves * sm_count());
-      const double cost = waste * (1.0 / cands[i] + 1.0 / 128.0) / eff;
+      const double cost = waste * (1.0 / cands[i] + (m_tiles >= 2 ? 1.0 / 256.0 : 1.0 / 128.0)) / eff;
       if (cost < best * 0.999) {
         best = cost;
         bn_sel = cands[i];
@@ -832,6 +859,24 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
     // limit is the ~60 B/clk each SM can ingest, which multicast does not reduce — so it is opt-in.
     int cs = 1;
     if (const char* f = getenv("IVV_CLUSTER")) cs = (atoi(f) == 2 && m_tiles >= 2) ? 2 : 1;
+    // CTA pairs (tcgen05.mma.cta_group::2, M = 256): default whenever there are at least two M tiles
+    bool pair = m_tiles >= 2;
+    if (const char* f = getenv("IVV_PAIR")) pair = pair && atoi(f) != 0;
+    if (pair && cs == 1) {
+#define IVV_PAIR_LAUNCH(BN_, ST_, CW_, GG_, TW_) \
+  return launch_persistent_cs<BN_, ST_, CW_, GG_, TW_, 2, true>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream)
+      if (a->geglu) IVV_PAIR_LAUNCH(256, 6, 32, true, true);
+      switch (bn_sel) {
+        case 256:
+          if (k_total >= 2560) IVV_PAIR_LAUNCH(256, 6, 64, false, false);
+          IVV_PAIR_LAUNCH(256, 5, 64, false, true);
+        case 160: IVV_PAIR_LAUNCH(160, 7, 32, false, true);
+        case 128: IVV_PAIR_LAUNCH(128, 8, 64, false, true);
+        case 64: IVV_PAIR_LAUNCH(64, 8, 32, false, true);
+        default: IVV_PAIR_LAUNCH(32, 8, 32, false, true);
+      }
+#undef IVV_PAIR_LAUNCH
+    }
     if (a->geglu) return launch_persistent<256, 4, 32, true, true>(tmA, tmB2, tmB, tmD, tmR, kp, m_tiles, n_tiles, cs, stream);
     switch (bn_sel) {
       case 256:
