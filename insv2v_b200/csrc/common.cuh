@@ -161,8 +161,10 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta_rank
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta_rank));
   return r;
 }
+// NB: no .release.cluster qualifier — ptxas turns that into MEMBAR + ERRBAR, which drains the thread's outstanding TMA
+// traffic and serialises a producer loop (measured: 2.2x slower pair-mode GEMM)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA loads of a CTA pair: data lands in the issuing CTA's shared memory, the bytes are counted on `bar_cluster_addr`
 // (the leader's barrier)

@@ -337,7 +337,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     tma_prefetch_desc(&tmD);
     tma_prefetch_desc(&tmR);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], TWO ? 2 : 1);      // pair mode: leader's expect_tx + the peer's remote arrive
+      mbar_init(&full_bar[s], 1);                // pair mode: the leader expects the bytes of both CTAs
       mbar_init(&empty_bar[s], TWO ? 1 : CS);    // multicast mode: every CTA must have consumed the stage
     }
     for (int b = 0; b < 2; ++b) {
@@ -379,9 +379,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
           if constexpr (TWO) {
-            // bytes of BOTH CTAs are counted on the leader's barrier; the peer announces itself with a remote arrive
+            // bytes of BOTH CTAs are counted on the leader's barrier. The peer needs no arrive of its own: it can only
+            // refill a stage after the leader's MMA released it, i.e. after the leader's barrier finished that phase.
             const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
-            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes); else mbar_arrive_cluster(lead_bar);
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);
             tma_load_4d_2sm(sa, &tmA, lead_bar, kb * kBlockK, w0 + dx, h0 + dy, n0);
             tma_load_3d_2sm(sa + kABytes, &tmB, lead_bar, kb * kBlockK, ntile * BN + crank * kBRows, tap);
             if (++stage == STAGES) {
