@@ -145,8 +145,14 @@ def top_gemm_roofline(pk):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     achieved = flops / (ms * 1e-3) / 1e12
-    return {"bound": "tensor", "kernel": "gemm_tc_kernel<160,3> conv3x3 320->320 [48,32,48]", "achieved": achieved,
-            "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"], "traffic": None,
+    traffic = None
+    tk = os.path.join(ROOT, "profiles", "r01_top_kernel.json")
+    if os.path.exists(tk):  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
+        j = json.load(open(tk))
+        traffic = j["dram_bytes_read"] + j["dram_bytes_write"]
+    return {"bound": "tensor", "kernel": "gemm_tc_persistent_kernel<160,...> conv3x3 320->320 on [48,32,48] frames",
+            "achieved": achieved,
+            "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"], "traffic": traffic,
             "peak_source": pk["src"] + ", burst (kernel timed alone)", "ms_per_launch": ms,
             "flops_per_launch": flops}
 
