@@ -179,3 +179,51 @@ def test_flow_utils_vs_reference_golden():
     assert warp_image(img[0], flow[0]).shape == (1, 4, 32, 48)  # 3-D inputs promoted (flow_utils.py:34-37)
     with pytest.raises(AssertionError):
         warp_image(img, flow[:2])
+
+
+def test_full_size_unet_vs_oracle():
+    """The REAL architecture (configs/instruct_v2v_inference.yaml: 320/640/1280/1280 channels, head dims 40/80/160,
+    1.28 G parameters) on an 8-frame 32x32 latent (config-1 shape, one CFG branch) against the CPU oracle."""
+    from insv2v_b200.unet import UNet3DConditionModel
+    O = _oracle()
+    cfg = O.UNET_CONFIG_FULL
+    sd = O.seeded_state_dict(schema("unet_full"), seed=7)
+    m = UNet3DConditionModel(**cfg)
+    m.load_state_dict(sd, strict=True)
+    m = m.half().cuda().eval()  # fp16 parameters, as the reference runs under fp16 autocast
+    x, ctx = seeded((1, 8, 8, 32, 32), 1), seeded((1, 77, 768), 2)
+    t = torch.tensor([501])
+    with torch.no_grad():
+        ref = O.unet3d_forward(sd, cfg, x, t, ctx)
+    y = m(x.cuda(), t.cuda(), encoder_hidden_states=ctx.cuda()).sample
+    assert y.dtype == torch.float32
+    _check("full-size unet [1,8,8,32,32]", y, ref)
+
+
+def test_full_size_config2_properties():
+    """Size-independent properties at BASELINE's full shape [3,8,16,32,48]: deterministic replay, independence of the
+    batch rows (identical CFG branches give bit-identical outputs), finite values."""
+    from insv2v_b200.unet import UNet3DConditionModel
+    O = _oracle()
+    torch.manual_seed(0)
+    m = UNet3DConditionModel(**O.UNET_CONFIG_FULL)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if "temporal_transformer.proj_out" in n:
+                p.normal_(0, 0.02)
+    m = m.cuda().eval()
+    one = seeded((1, 8, 16, 32, 48), 3).cuda()
+    x = one.repeat(3, 1, 1, 1, 1)
+    c1 = seeded((1, 77, 768), 4).cuda()
+    ctx = c1.repeat(3, 1, 1)
+    t = torch.full((3,), 981, device="cuda")
+    y1 = m(x, t, encoder_hidden_states=ctx).sample
+    y2 = m(x, t, encoder_hidden_states=ctx).sample
+    assert y1.shape == (3, 4, 16, 32, 48) and torch.isfinite(y1).all()
+    assert torch.equal(y1, y2), "replay is not deterministic"
+    assert torch.equal(y1[0], y1[1]) and torch.equal(y1[1], y1[2]), "batch rows are not independent"
+    # a different context in branch 2 must change branch 2 only
+    ctx2 = ctx.clone()
+    ctx2[2] = seeded((77, 768), 5).cuda()
+    y3 = m(x, t, encoder_hidden_states=ctx2).sample
+    assert torch.equal(y3[0], y1[0]) and not torch.equal(y3[2], y1[2])

@@ -10,7 +10,7 @@ sys.path.insert(0, ROOT)
 
 SHAPES = [(73728, 320, 320, 1), (73728, 320, 960, 1), (73728, 1280, 320, 1), (18432, 640, 640, 1), (18432, 640, 1920, 1),
           (4608, 1280, 1280, 1), (4608, 1280, 3840, 1), (1152, 1280, 1280, 9), (4608, 1280, 1280, 9),
-          (73728, 320, 320, 9)]
+          (73728, 320, 320, 9), (18432, 640, 640, 9), (16384, 512, 512, 9)]
 
 
 def child():
@@ -25,7 +25,7 @@ def child():
             geo = dict(n_img=1, h=1, w=rows)
         else:
             w = ops.pack_conv3x3(torch.randn(n, k, 3, 3, device=dev) * 0.01)
-            hw = {73728: (48, 32, 48), 18432: (48, 16, 24), 4608: (48, 8, 12), 1152: (48, 4, 6)}[rows]
+            hw = {73728: (48, 32, 48), 18432: (48, 16, 24), 4608: (48, 8, 12), 1152: (48, 4, 6), 16384: (16, 32, 32)}[rows]
             geo = dict(n_img=hw[0], h=hw[1], w=hw[2])
         for i in range(nbuf):
             ops.gemm(xs[i], w, c=k, taps=taps, out=outs[i], **geo)
@@ -46,8 +46,10 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
     else:
-        for bn in ["auto", "64", "128", "160", "256"]:
-            env = dict(os.environ)
-            if bn != "auto":
-                env["IVV_FORCE_BN"] = bn
-            subprocess.run([sys.executable, __file__, "child"], env=env)
+        for pair in ["1", "0"]:
+            for bn in ["auto", "128", "160", "256"]:
+                env = dict(os.environ, IVV_PAIR=pair)
+                if bn != "auto":
+                    env["IVV_FORCE_BN"] = bn
+                print(f"--- IVV_PAIR={pair}", flush=True)
+                subprocess.run([sys.executable, __file__, "child"], env=env)
