@@ -24,6 +24,7 @@ struct GemmKParams {
   int n_out;                      // GEMM N (weight rows)
   int out_cols;                   // columns written (n_out, or n_out/2 for GEGLU)
   int geglu, out_f32;
+  int dbg_skip;                   // tuning only (IVV_DEBUG_SKIP): 1 = no MMA issue, 2 = no TMA loads (results are garbage)
   void* d;
   long long d_ld;
   const __half* bias;
@@ -391,6 +392,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             }
             continue;
           }
+          if (p.dbg_skip == 2) {
+            mbar_arrive(&full_bar[stage]);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           mbar_expect_tx(&full_bar[stage], kStageBytes);
           tma_load_4d(sa, &tmA, &full_bar[stage], kb * kBlockK, w0 + dx, h0 + dy, n0);
           if constexpr (CS > 1)
@@ -425,6 +434,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           const uint64_t bdesc = umma_desc_kmajor_sw128(sa + kABytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
+            if (p.dbg_skip == 1 && (it | k) != 0) continue;
             if constexpr (TWO) umma_f16_ss_2sm(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
             else umma_f16_ss(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
           }
@@ -772,6 +782,7 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
   kp.geglu = a->geglu;
   kp.out_cols = a->geglu ? (int)(a->n_out / 2) : (int)a->n_out;
   kp.out_f32 = a->out_f32;
+  if (const char* f = getenv("IVV_DEBUG_SKIP")) kp.dbg_skip = atoi(f);
   kp.d = a->d;
   kp.d_ld = a->d_ld;
   kp.bias = reinterpret_cast<const __half*>(a->bias);
