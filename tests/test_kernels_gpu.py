@@ -333,3 +333,53 @@ def test_cfg_ddim_step():
     ref = ap ** 0.5 * x0 + (1 - ap) ** 0.5 * e
     got = ops.cfg_ddim_step_(eps3, lat.clone(), 7.5, 1.5, at, ap)
     report("cfg_ddim", got, ref, rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ kernel variants
+_VARIANT_SNIPPET = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from insv2v_b200 import ops
+torch.manual_seed(0)
+dev = "cuda"
+# conv 3x3 + bias + residual (persistent GEMM variants)
+n, ci, co, h, w = 6, 320, 320, 32, 48
+x = torch.randn(n, ci, h, w, device=dev).half(); wt = (torch.randn(co, ci, 3, 3, device=dev) * (9 * ci) ** -0.5).half()
+b = torch.randn(co, device=dev).half(); res = torch.randn(n, co, h, w, device=dev).half()
+fr = lambda t: t.permute(0, 2, 3, 1).reshape(-1, t.shape[1]).contiguous()
+out = ops.conv3x3(fr(x), ops.pack_conv3x3(wt), n, h, w, bias=b, residual=fr(res))
+ref = torch.nn.functional.conv2d(x.double(), wt.double(), b.double(), padding=1) + res.double()
+err = (out.reshape(n, h, w, co).permute(0, 3, 1, 2).double() - ref).abs()
+assert (err <= 1e-4 + 1e-3 * ref.abs()).all(), float(err.max())
+# odd number of M tiles (ghost tile of a CTA pair) and GEGLU
+rows, c = 128 * 5, 320
+xl = torch.randn(rows, c, device=dev).half(); wl = (torch.randn(8 * c, c, device=dev) * c ** -0.5).half()
+bl = (torch.randn(8 * c, device=dev) * 0.1).half()
+wp, bp = ops.pack_geglu(wl, bl)
+o = ops.linear(xl, wp, bias=bp, geglu=True)
+y = xl.double() @ wl.double().t() + bl.double(); hid, gate = y.chunk(2, dim=-1)
+refg = hid * torch.nn.functional.gelu(gate)
+assert ((o.double() - refg).abs() <= 1e-4 + 1e-3 * refg.abs()).all()
+# self-attention S=640, d=40
+nb, s, heads, d = 2, 640, 8, 40
+qkv = torch.randn(nb * s, 3 * heads * d, device=dev).half(); C = heads * d
+a = ops.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], n_batch=nb, s_q=s, s_kv=s, heads=heads, d=d, q_ld=3 * C, kv_ld=3 * C)
+q, k, v = (t.float().reshape(nb, s, heads, d).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
+ra = (torch.softmax(q @ k.transpose(-1, -2) * d ** -0.5, -1) @ v).transpose(1, 2).reshape(nb * s, C)
+assert ((a.float() - ra).abs() <= 5e-4 + 2e-3 * ra.abs()).all()
+print("variant ok")
+"""
+
+
+@pytest.mark.parametrize("env", [{"IVV_PAIR": "0"}, {"IVV_PAIR": "0", "IVV_CLUSTER": "2"}, {"IVV_ATTN_TWO_TILE": "1"},
+                                 {"IVV_FORCE_BN": "128"}, {"IVV_FORCE_BN": "256"}])
+def test_kernel_variants(env):
+    """The opt-in / fallback code paths (single-CTA GEMM, multicast clusters, two-tile attention, other tile widths)
+    stay correct: same checks in a subprocess with the tuning environment variables set."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _VARIANT_SNIPPET % root], env=dict(os.environ, **env),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "variant ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
