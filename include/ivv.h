@@ -43,7 +43,8 @@ typedef struct {
   void* d;            /* fp16 (or fp32 when out_f32) [n_img*h*w, d_ld]                                         */
   int64_t d_ld;
   int32_t out_f32;
-  int32_t reserved;
+  int32_t splits;     /* split-K: >1 -> d is fp32 [splits, rows, d_ld] partial sums (no epilogue terms);        */
+                      /* finish with ivv_splitk_reduce. 0/1 = off                                                */
   const void* bias;     /* fp16 [n_out] or NULL (GEGLU: same tile-interleaved order as wgt rows)               */
   const void* rowbias;  /* fp16 [groups, rowbias_ld] or NULL: added to every pixel of group pix/rowbias_group  */
   int64_t rowbias_group, rowbias_ld;
@@ -51,6 +52,11 @@ typedef struct {
   int64_t res_ld;
 } ivv_gemm_args;
 int ivv_gemm(const ivv_gemm_args* args, ivv_stream_t stream);
+
+/* split-K finish: out[r, c] = sum_z partial[z][r][c] (+bias[c]) (+rowbias[r/group][c]) (+residual[r][c]) -> fp16.   */
+int ivv_splitk_reduce(const float* partial, int32_t splits, int64_t rows, int64_t n, int64_t p_ld, const void* bias,
+                      const void* rowbias, int64_t rowbias_group, int64_t rowbias_ld, const void* residual,
+                      int64_t res_ld, void* out, int64_t out_ld, ivv_stream_t stream);
 
 /* im2col for the stride-2 3x3 convolutions: out[n,ho,wo, tap*c + ci] = x[n, 2ho+ky-pad, 2wo+kx-pad, ci].
  * pad = 1: Downsample3D (resnet.py:99-107, symmetric pad 1);  pad = 0: the VAE encoder's Downsample

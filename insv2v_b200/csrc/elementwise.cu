@@ -144,6 +144,49 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ eps3, float* __restric
   }
 }
 
+// split-K finish: 8 columns per thread, fp32 partial planes summed in a fixed order (deterministic)
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long rows, int n, long long p_ld,
+                                     const __half* __restrict__ bias, const __half* __restrict__ rowbias,
+                                     long long rowbias_group, long long rowbias_ld, const __half* __restrict__ residual,
+                                     long long res_ld, __half* __restrict__ out, long long out_ld) {
+  const int V = n / 8;
+  const long long total = rows * V;
+  const long long plane = rows * p_ld;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int vec = (int)(i % V);
+    const long long r = i / V;
+    const int c = vec * 8;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int z = 0; z < splits; ++z) {
+      const float4 a0 = *reinterpret_cast<const float4*>(partial + z * plane + r * p_ld + c);
+      const float4 a1 = *reinterpret_cast<const float4*>(partial + z * plane + r * p_ld + c + 4);
+      acc[0] += a0.x, acc[1] += a0.y, acc[2] += a0.z, acc[3] += a0.w;
+      acc[4] += a1.x, acc[5] += a1.y, acc[6] += a1.z, acc[7] += a1.w;
+    }
+    auto add8 = [&](const __half* src) {
+      const uint4 u = *reinterpret_cast<const uint4*>(src);
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
+      }
+    };
+    if (bias) add8(bias + c);
+    if (rowbias) add8(rowbias + (r / rowbias_group) * rowbias_ld + c);
+    if (residual) add8(residual + r * res_ld + c);
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+    *reinterpret_cast<uint4*>(out + r * out_ld + c) = o;
+  }
+}
+
 static inline unsigned grid_for(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
   const long long cap = 148LL * 16;
@@ -156,6 +199,23 @@ static inline unsigned grid_for(long long total, int threads) {
 
 using namespace ivv;
 #define STREAM reinterpret_cast<cudaStream_t>(stream_)
+
+extern "C" int ivv_splitk_reduce(const float* partial, int32_t splits, int64_t rows, int64_t n, int64_t p_ld,
+                                 const void* bias, const void* rowbias, int64_t rowbias_group, int64_t rowbias_ld,
+                                 const void* residual, int64_t res_ld, void* out, int64_t out_ld,
+                                 ivv_stream_t stream_) {
+  IVV_REQUIRE(partial && out && splits >= 1 && rows > 0 && n > 0, "ivv_splitk_reduce: bad arguments");
+  IVV_REQUIRE(n % 8 == 0 && p_ld % 4 == 0 && out_ld % 8 == 0, "ivv_splitk_reduce: n, out_ld must be multiples of 8");
+  IVV_REQUIRE(!rowbias || (rowbias_group > 0 && rowbias_ld % 8 == 0), "ivv_splitk_reduce: bad rowbias geometry");
+  IVV_REQUIRE(!residual || res_ld % 8 == 0, "ivv_splitk_reduce: res_ld must be a multiple of 8");
+  const long long total = rows * (n / 8);
+  splitk_reduce_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(
+      partial, splits, rows, (int)n, p_ld, reinterpret_cast<const __half*>(bias),
+      reinterpret_cast<const __half*>(rowbias), rowbias_group > 0 ? rowbias_group : 1, rowbias_ld,
+      reinterpret_cast<const __half*>(residual), res_ld, reinterpret_cast<__half*>(out), out_ld);
+  IVV_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int ivv_im2col_s2(const void* x, void* out, int64_t n_img, int64_t h, int64_t w, int64_t c, int64_t ho,
                              int64_t wo, int32_t pad, ivv_stream_t stream_) {

@@ -24,6 +24,8 @@ struct GemmKParams {
   int n_out;                      // GEMM N (weight rows)
   int out_cols;                   // columns written (n_out, or n_out/2 for GEGLU)
   int geglu, out_f32;
+  int splits;                     // split-K (v1 kernel): blockIdx.z owns a contiguous range of (tap, k-block) iterations
+  long long split_stride;         // elements between the fp32 partial planes
   int dbg_skip;                   // tuning only (IVV_DEBUG_SKIP): 1 = no MMA issue, 2 = no TMA loads (results are garbage)
   void* d;
   long long d_ld;
@@ -113,7 +115,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tg = mtile / (p.tiles_w * p.tiles_h);
   const int w0 = tw * p.bw, h0 = th * p.bh;
       const int n0 = mtile < p.tiles_w * p.tiles_h * p.tiles_g ? tg * p.bn : p.NI;  // ghost tile of an odd cluster: fully out of bounds
-  const int total_it = p.taps * p.kblocks;
+  const int all_it = p.taps * p.kblocks;
+  const int per_split = (all_it + p.splits - 1) / p.splits;
+  const int it_begin = blockIdx.z * per_split;
+  const int total_it = min(all_it, it_begin + per_split) - it_begin;  // iterations of this split (>= 1 by construction)
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -137,8 +142,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int it = 0; it < total_it; ++it) {
-        const int tap = it / p.kblocks;
-        const int kb = it - tap * p.kblocks;
+        const int tap = (it_begin + it) / p.kblocks;
+        const int kb = (it_begin + it) - tap * p.kblocks;
         int dy = 0, dx = 0;
         if (p.taps == 9) {
           dy = tap / 3 - 1;
@@ -191,7 +196,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int w = w0 + wi, h = h0 + hi, n = n0 + ni;
     const bool valid = (w < p.W) && (h < p.H) && (n < p.NI);
     const long long pix = (static_cast<long long>(n) * p.H + h) * p.W + w;
-    const bool d_vec = (p.d_ld % 8) == 0 && ((reinterpret_cast<uintptr_t>(p.d) & 31) == 0);
+    void* dptr = p.splits > 1 ? static_cast<void*>(reinterpret_cast<float*>(p.d) + blockIdx.z * p.split_stride) : p.d;
+    const bool d_vec = (p.d_ld % 8) == 0 && ((reinterpret_cast<uintptr_t>(dptr) & 31) == 0);
     const bool r_vec = p.residual && (p.res_ld % 8) == 0 && ((reinterpret_cast<uintptr_t>(p.residual) & 15) == 0);
     const __half* rb = p.rowbias ? p.rowbias + (pix / p.rowbias_group) * p.rowbias_ld : nullptr;
 
@@ -231,7 +237,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] += rv[j];
             }
-            store8(p.d, p.out_f32 != 0, pix * p.d_ld + col, v, nv, d_vec);
+            store8(dptr, p.out_f32 != 0, pix * p.d_ld + col, v, nv, d_vec);
           }
         }
       }
@@ -263,7 +269,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
               v[j] = hv * gelu_erf_f(gv);
             }
-            store8(p.d, p.out_f32 != 0, pix * p.d_ld + ocol, v, nv, d_vec);
+            store8(dptr, p.out_f32 != 0, pix * p.d_ld + ocol, v, nv, d_vec);
           }
         }
       }
@@ -747,7 +753,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKPar
     IVV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid(n_tiles, m_tiles, 1);
+  dim3 grid(n_tiles, m_tiles, kp.splits);
   gemm_tc_kernel<BN, STAGES><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, kp);
   IVV_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -783,6 +789,16 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
   kp.out_cols = a->geglu ? (int)(a->n_out / 2) : (int)a->n_out;
   kp.out_f32 = a->out_f32;
   if (const char* f = getenv("IVV_DEBUG_SKIP")) kp.dbg_skip = atoi(f);
+  kp.splits = a->splits > 1 ? a->splits : 1;
+  kp.split_stride = (long long)a->n_img * a->h * a->w * a->d_ld;
+  if (kp.splits > 1) {
+    IVV_REQUIRE(a->out_f32 && !a->geglu && !a->bias && !a->rowbias && !a->residual,
+                "ivv_gemm: split-K writes raw fp32 partial sums (no epilogue terms, out_f32 = 1)");
+    IVV_REQUIRE(kp.splits <= kp.taps * kp.kblocks && kp.splits <= 64, "ivv_gemm: too many splits (%d)", kp.splits);
+    // every split must own at least one iteration
+    const int all_it = kp.taps * kp.kblocks, per = (all_it + kp.splits - 1) / kp.splits;
+    IVV_REQUIRE((kp.splits - 1) * per < all_it, "ivv_gemm: splits (%d) leave an empty K range", kp.splits);
+  }
   kp.d = a->d;
   kp.d_ld = a->d_ld;
   kp.bias = reinterpret_cast<const __half*>(a->bias);
@@ -808,7 +824,7 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
     for (int i = 0; i < 5; ++i) {
       const long long nt = (a->n_out + cands[i] - 1) / cands[i];
       const double waste = (double)nt * cands[i] / (double)a->n_out;
-      const long long tiles = nt * m_tiles;
+      const long long tiles = nt * m_tiles * (a->splits > 1 ? a->splits : 1);
       const long long waves = (tiles + sm_count() - 1) / sm_count();
       const double eff = (double)tiles / (double)(waves * sm_count());
       const double cost = waste * (1.0 / cands[i] + (m_tiles >= 2 ? 1.0 / 256.0 : 1.0 / 128.0)) / eff;

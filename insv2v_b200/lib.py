@@ -19,7 +19,7 @@ class GemmArgs(ctypes.Structure):
         ("a", c_void_p), ("n_img", c_i64), ("h", c_i64), ("w", c_i64), ("c", c_i64), ("a_ld", c_i64),
         ("wgt", c_void_p), ("n_out", c_i64), ("w_ld", c_i64),
         ("taps", c_i32), ("geglu", c_i32),
-        ("d", c_void_p), ("d_ld", c_i64), ("out_f32", c_i32), ("reserved", c_i32),
+        ("d", c_void_p), ("d_ld", c_i64), ("out_f32", c_i32), ("splits", c_i32),
         ("bias", c_void_p), ("rowbias", c_void_p), ("rowbias_group", c_i64), ("rowbias_ld", c_i64),
         ("residual", c_void_p), ("res_ld", c_i64),
     ]
@@ -30,6 +30,8 @@ SIGNATURES = {
     "ivv_abi_version": (c_i32, []),
     "ivv_last_error": (ctypes.c_char_p, []),
     "ivv_gemm": (c_i32, [ctypes.POINTER(GemmArgs), c_void_p]),
+    "ivv_splitk_reduce": (c_i32, [c_void_p, c_i32, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_i64, c_i64, c_void_p,
+                                  c_i64, c_void_p, c_i64, c_void_p]),
     "ivv_im2col_s2": (c_i32, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i32, c_void_p]),
     "ivv_groupnorm": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i32, c_i64, c_f32, c_i32,
                               c_void_p, c_size, c_void_p]),

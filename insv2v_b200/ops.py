@@ -118,8 +118,19 @@ def pack_geglu(w, b):
 # ----------------------------------------------------------------------------------------------------------------
 # GEMM / conv
 # ----------------------------------------------------------------------------------------------------------------
+SPLITK = True  # module switch (tests / tuning)
+
+
+def _splitk_policy(rows, k_total, n_out):
+    """Number of K splits: only when the output has too few 128x128 tiles to fill the SMs and K is long."""
+    if rows > 2304 or k_total < 4096 or n_out % 8 != 0:
+        return 1
+    tiles = ((rows + 127) // 128) * ((n_out + 127) // 128)
+    return max(1, min(296 // tiles, k_total // 1024, 8))
+
+
 def gemm(a, wgt, *, n_img, h, w, c, n_out=None, taps=1, a_ld=None, bias=None, rowbias=None, rowbias_group=0,
-         residual=None, geglu=False, out=None, out_f32=False):
+         residual=None, geglu=False, out=None, out_f32=False, _splits=1):
     """D = conv/linear(A, W) with fused epilogue; A rows are pixels [n_img*h*w, a_ld], W packed by pack_*()."""
     _chk16(a, "a"), _chk16(wgt, "wgt"), _chk16(bias, "bias"), _chk16(rowbias, "rowbias"), _chk16(residual, "residual")
     if wgt.dim() != 3 or wgt.shape[0] != taps:
@@ -128,6 +139,20 @@ def gemm(a, wgt, *, n_img, h, w, c, n_out=None, taps=1, a_ld=None, bias=None, ro
     a_ld = a.shape[-1] if a_ld is None else a_ld
     rows = n_img * h * w
     cols = n_out // 2 if geglu else n_out
+    # split-K for the few-row / long-K convolutions of the 4x6 and 8x12 levels: too few output tiles for 148 SMs
+    splits = _splitk_policy(rows, c * taps, n_out) if (SPLITK and not geglu and not out_f32 and
+                                                        (out is None or out.dtype == F16)) else 1
+    if splits > 1:
+        partial = empty((splits, rows, n_out), torch.float32, a.device)
+        gemm(a, wgt, n_img=n_img, h=h, w=w, c=c, n_out=n_out, taps=taps, a_ld=a_ld, out=partial, _splits=splits)
+        if out is None:
+            out = empty((rows, n_out), F16, a.device)
+        _lib.check(_lib.load().ivv_splitk_reduce(
+            _p(partial), splits, rows, n_out, n_out, _p(bias), _p(rowbias), rowbias_group if rowbias is not None else 1,
+            rowbias.shape[-1] if rowbias is not None else 0, _p(residual),
+            residual.shape[-1] if residual is not None else 0, _p(out), out.shape[-1], _s()), "ivv_splitk_reduce")
+        _count()
+        return out
     if out is None:
         out = empty((rows, cols), torch.float32 if out_f32 else F16, a.device)
     args = _lib.GemmArgs()
@@ -135,6 +160,7 @@ def gemm(a, wgt, *, n_img, h, w, c, n_out=None, taps=1, a_ld=None, bias=None, ro
     args.wgt, args.n_out, args.w_ld = wgt.data_ptr(), n_out, wgt.shape[2]
     args.taps, args.geglu = taps, int(geglu)
     args.d, args.d_ld, args.out_f32 = out.data_ptr(), out.shape[-1], int(out.dtype == torch.float32)
+    args.splits = _splits
     args.bias = bias.data_ptr() if bias is not None else None
     if rowbias is not None:
         args.rowbias, args.rowbias_group, args.rowbias_ld = rowbias.data_ptr(), rowbias_group, rowbias.shape[-1]

@@ -383,3 +383,24 @@ def test_kernel_variants(env):
     r = subprocess.run([sys.executable, "-c", _VARIANT_SNIPPET % root], env=dict(os.environ, **env),
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "variant ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("n,ci,co,h,w", [(48, 1280, 1280, 4, 6), (48, 2560, 1280, 4, 6), (3, 640, 320, 8, 12)])
+def test_conv3x3_splitk(n, ci, co, h, w):
+    """Few-row / long-K convolutions go through the split-K path (fp32 partial planes + deterministic reduce) with the
+    same fused terms as the direct epilogue."""
+    ops = _ops()
+    assert ops._splitk_policy(n * h * w, 9 * ci, co) > 1
+    x = h16(n, ci, h, w, seed=1)
+    wt = h16(co, ci, 3, 3, scale=(9 * ci) ** -0.5, seed=2)
+    b, res = h16(co, seed=3), h16(n, co, h, w, seed=5)
+    temb = h16(3, co, seed=4)
+    f = n // 3
+    out = ops.conv3x3(_frames(x), ops.pack_conv3x3(wt), n, h, w, bias=b, rowbias=temb, rowbias_group=f * h * w,
+                      residual=_frames(res))
+    ref = F.conv2d(x.double(), wt.double(), b.double(), padding=1) + res.double() \
+        + temb.double().repeat_interleave(f, dim=0)[:, :, None, None]
+    report(f"conv3x3 split-K {ci}->{co} {h}x{w}", _nchw(out, n, h, w), ref)
+    out2 = ops.conv3x3(_frames(x), ops.pack_conv3x3(wt), n, h, w, bias=b, rowbias=temb, rowbias_group=f * h * w,
+                       residual=_frames(res))
+    assert torch.equal(out, out2)  # fixed-order reduction: bit-reproducible
