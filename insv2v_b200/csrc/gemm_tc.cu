@@ -26,6 +26,8 @@ struct GemmKParams {
   int geglu, out_f32;
   int splits;                     // split-K (v1 kernel): blockIdx.z owns a contiguous range of (tap, k-block) iterations
   long long split_stride;         // elements between the fp32 partial planes
+  int ws_stages;                  // >0: weight-stationary mode (persistent kernel): the CTA's weight tile (all of K) is
+                                  // loaded once and stays in shared memory; only A tiles stream through ws_stages slots
   int dbg_skip;                   // tuning only (IVV_DEBUG_SKIP): 1 = no MMA issue, 2 = no TMA loads (results are garbage)
   void* d;
   long long d_ld;
@@ -332,11 +334,17 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   uint64_t* tmem_full_bar = empty_bar + STAGES;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
   uint64_t* res_bar = tmem_empty_bar + 2;        // [2] residual tile landed (one per epilogue group)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_bar + 2);
+  uint64_t* b_full = res_bar + 2;                // weight-stationary mode: resident weight tile landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int its_per_tile = p.taps * p.kblocks;
+  // weight-stationary layout of the same stage region: [its_per_tile x (BN x 128 B) resident B][ws_stages x 16 KB A ring]
+  const bool ws = !TWO && CS == 1 && p.ws_stages > 0;
+  uint8_t* b_res = smem;
+  uint8_t* a_ring = smem + its_per_tile * (BN * 128);
+  const int nstages = ws ? p.ws_stages : STAGES;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
@@ -352,6 +360,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       mbar_init(&tmem_empty_bar[b], TWO ? 16 : 8);  // one arrive per epilogue warp (of both CTAs in pair mode)
       mbar_init(&res_bar[b], 1);
     }
+    mbar_init(b_full, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -367,6 +376,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       // ===== TMA producer =====
       int stage = 0;
       uint32_t phase = 0;
+      if (ws) {  // gridDim.x is a multiple of n_tiles, so every tile of this CTA has the same N tile
+        const int ntile0 = blockIdx.x % n_tiles;
+        mbar_expect_tx(b_full, its_per_tile * BN * 128);
+        for (int it = 0; it < its_per_tile; ++it) {
+          const int tap = it / p.kblocks;
+          tma_load_3d(b_res + it * (BN * 128), &tmB, b_full, (it - tap * p.kblocks) * kBlockK, ntile0 * BN, tap);
+        }
+      }
       for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
         const int ntile = tile % n_tiles;
         const int mtile = (tile / n_tiles) * CS + crank;
@@ -393,6 +410,15 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             tma_load_4d_2sm(sa, &tmA, lead_bar, kb * kBlockK, w0 + dx, h0 + dy, n0);
             tma_load_3d_2sm(sa + kABytes, &tmB, lead_bar, kb * kBlockK, ntile * BN + crank * kBRows, tap);
             if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
+          if (ws) {
+            mbar_expect_tx(&full_bar[stage], kABytes);
+            tma_load_4d(a_ring + stage * kABytes, &tmA, &full_bar[stage], kb * kBlockK, w0 + dx, h0 + dy, n0);
+            if (++stage == nstages) {
               stage = 0;
               phase ^= 1;
             }
@@ -427,6 +453,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
+      if (ws) mbar_wait(b_full, 0);
       for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++local) {
         const int buf = local & 1;
         mbar_wait(&tmem_empty_bar[buf], ((local >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
@@ -435,9 +462,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         for (int it = 0; it < its_per_tile; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * kStageBytes);
+          const uint32_t sa = ws ? smem_u32(a_ring + stage * kABytes) : smem_u32(smem + stage * kStageBytes);
           const uint64_t adesc = umma_desc_kmajor_sw128(sa);
-          const uint64_t bdesc = umma_desc_kmajor_sw128(sa + kABytes);
+          const uint64_t bdesc = umma_desc_kmajor_sw128(ws ? smem_u32(b_res + it * (BN * 128)) : sa + kABytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             if (p.dbg_skip == 1 && (it | k) != 0) continue;
@@ -447,7 +474,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           if constexpr (TWO) umma_commit_2sm(&empty_bar[stage], kMask);
           else if constexpr (CS > 1) umma_commit_multicast(&empty_bar[stage], kMask);
           else umma_commit(&empty_bar[stage]);
-          if (++stage == STAGES) {
+          if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
           }
@@ -634,7 +661,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       if constexpr (TILEWIDE) {
         fence_proxy_async_smem();
         named_bar_sync(1 + g, 128);
-        if (issuer) {
+        if (issuer && p.dbg_skip != 3) {
           for (int chunk = g; chunk < NCHUNK; chunk += 2)
             tma_store_4d(&tmD, staging + chunk * kChunkBytes, ntile * OUT_W + chunk * CW, w0, h0, n0);
           bulk_commit_group();
@@ -718,6 +745,7 @@ static int launch_persistent_cs(const CUtensorMap& tmA, const CUtensorMap& tmB, 
   const int total = groups * n_tiles;  // (super) tiles
   int clusters = sm_count() / CS;
   if (clusters > total) clusters = total;
+  if (kp.ws_stages > 0) clusters = (sm_count() / n_tiles) * n_tiles;  // weight-stationary: one N tile per CTA
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(clusters * CS));
   cfg.blockDim = dim3(kPersistThreads);
@@ -887,8 +915,19 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
     // limit is the ~60 B/clk each SM can ingest, which multicast does not reduce — so it is opt-in.
     int cs = 1;
     if (const char* f = getenv("IVV_CLUSTER")) cs = (atoi(f) == 2 && m_tiles >= 2) ? 2 : 1;
+    // Weight-stationary mode for short-K GEMMs with many M tiles (the K = 320 linears of the 32x48 level): the weight
+    // tile of a CTA (all of K) stays in shared memory, only activations stream -> 2.25x less operand ingest per tile.
+    {
+      const int stages = bn_sel == 256 ? 3 : bn_sel == 160 ? 5 : 6;  // stage counts of the single-CTA configs below
+      const long long region = (long long)stages * (kABytes + bn_sel * 128);
+      const long long b_res = (long long)kp.taps * kp.kblocks * bn_sel * 128;
+      const long long a_slots = (region - b_res) / kABytes;
+      const bool ws_ok = !a->geglu && bn_sel >= 128 && a_slots >= 4 && n_tiles <= sm_count() / 2 &&
+                         (long long)m_tiles * n_tiles >= 4LL * sm_count() && getenv("IVV_NO_WS") == nullptr;
+      kp.ws_stages = ws_ok ? (int)(a_slots < stages ? a_slots : stages) : 0;
+    }
     // CTA pairs (tcgen05.mma.cta_group::2, M = 256): default whenever there are at least two M tiles
-    bool pair = m_tiles >= 2;
+    bool pair = m_tiles >= 2 && kp.ws_stages == 0;
     if (const char* f = getenv("IVV_PAIR")) pair = pair && atoi(f) != 0;
     if (pair && cs == 1) {
 #define IVV_PAIR_LAUNCH(BN_, ST_, CW_, GG_, TW_) \

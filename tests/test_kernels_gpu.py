@@ -45,7 +45,8 @@ def h16(*shape, scale=1.0, seed=0):
 
 # ------------------------------------------------------------------------------------------------ GEMM / linear
 @pytest.mark.parametrize("rows,k,n", [(128, 64, 128), (300, 320, 320), (1000, 1280, 640), (77 * 3, 768, 2560),
-                                      (3, 320, 1280), (4608, 2560, 1280), (130, 72, 40)])
+                                      (3, 320, 1280), (4608, 2560, 1280), (130, 72, 40),
+                                      (73728, 320, 320), (40000, 320, 960), (50000, 256, 128)])  # weight-stationary
 def test_linear(rows, k, n):
     ops = _ops()
     x = h16(rows, k, seed=1)

@@ -8,8 +8,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-SHAPES = [(73728, 320, 320, 9), (73728, 320, 320, 1), (73728, 320, 960, 1), (18432, 640, 640, 9), (4608, 1280, 3840, 1),
-          (16384, 512, 512, 9)]
+SHAPES = [(73728, 320, 320, 9), (73728, 320, 320, 1), (73728, 320, 960, 1), (18432, 640, 640, 1), (4608, 1280, 1280, 1),
+          (4608, 1280, 3840, 1)]
 
 
 def child():
@@ -43,8 +43,6 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         child()
     else:
-        for pair in ["0", "1"]:
-            for skip in ["0", "1", "2"]:
-                if pair == "1" and skip == "2":
-                    continue  # the no-TMA hook exists only in the single-CTA producer
+        for pair in ["0"]:
+            for skip in ["0", "1", "2", "3"]:
                 subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, IVV_PAIR=pair, IVV_DEBUG_SKIP=skip))
