@@ -5,6 +5,7 @@
 
 #include "../../include/ivv.h"
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace ivv {
 
@@ -60,6 +61,14 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   IVV_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
   return 0;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("IVV_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 }  // namespace ivv

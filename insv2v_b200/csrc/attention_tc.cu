@@ -265,6 +265,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tmem_S = tmem_base;
   const uint32_t tmem_O = tmem_base + 128;
+  griddep_sync();
 
   if (warp == 4) {
     if (lane == 0) {
@@ -403,6 +404,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  griddep_sync();
 
   if (warp == 8) {
     if (lane == 0) {
@@ -505,8 +507,7 @@ static int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
     IVV_CHECK_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  attention_tc2_kernel<NS><<<grid, kAttn2Threads, smem, stream>>>(tq, tk, tv, ap);
-  IVV_CHECK_CUDA(cudaGetLastError());
+  IVV_CHECK_CUDA(launch_pdl(attention_tc2_kernel<NS>, grid, dim3(kAttn2Threads), smem, stream, tq, tk, tv, ap));
   return 0;
 }
 
@@ -520,8 +521,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
         cudaFuncSetAttribute(attention_tc_kernel<DC, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  attention_tc_kernel<DC, NS><<<grid, kAttnThreads, smem, stream>>>(tq, tk, tv, ap);
-  IVV_CHECK_CUDA(cudaGetLastError());
+  IVV_CHECK_CUDA(launch_pdl(attention_tc_kernel<DC, NS>, grid, dim3(kAttnThreads), smem, stream, tq, tk, tv, ap));
   return 0;
 }
 

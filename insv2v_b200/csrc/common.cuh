@@ -33,9 +33,36 @@ void set_error(const char* fmt, ...);
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                   const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
+// host: programmatic dependent launch (PDL). Every kernel launched through launch_pdl() executes griddep_sync() before
+// its first global-memory access, so kernel N+1's launch latency and prologue (barrier init, TMEM alloc, descriptor
+// prefetch) overlap kernel N's tail; the chain stays ordered because each kernel only completes after its own wait.
+// IVV_PDL=0 turns the launch attribute off (plain stream order) - the device-side wait is then a no-op.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------
+// PDL, device side: block until the preceding kernel in the stream has completed and its writes are visible, then let
+// the following kernel start launching. Must run before the first read or write of global memory.
+__device__ __forceinline__ void griddep_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -8,6 +8,7 @@ namespace ivv {
 // out[n, ho, wo, tap*c + ci] = x[n, 2*ho + ky - pad, 2*wo + kx - pad, ci]  (zero outside), tap = ky*3+kx
 __global__ void im2col_s2_kernel(const __half* __restrict__ x, __half* __restrict__ out, long long n_img, int h, int w,
                                  int c, int ho, int wo, int pad) {
+  griddep_sync();
   const int V = c / 8;
   const long long total = n_img * ho * wo * 9 * V;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -31,6 +32,7 @@ __global__ void im2col_s2_kernel(const __half* __restrict__ x, __half* __restric
 
 __global__ void upsample_nearest_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long n_img, int h,
                                         int w, int c, int ho, int wo) {
+  griddep_sync();
   const int V = c / 8;
   const long long total = n_img * ho * wo * V;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -50,6 +52,7 @@ __global__ void upsample_nearest_kernel(const __half* __restrict__ x, __half* __
 
 __global__ void concat_channels_kernel(const __half* __restrict__ a, int ca, const __half* __restrict__ b, int cb,
                                        __half* __restrict__ y, long long rows) {
+  griddep_sync();
   const int Va = ca / 8, Vb = cb / 8, V = Va + Vb;
   const long long total = rows * V;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -149,6 +152,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
                                      const __half* __restrict__ bias, const __half* __restrict__ rowbias,
                                      long long rowbias_group, long long rowbias_ld, const __half* __restrict__ residual,
                                      long long res_ld, __half* __restrict__ out, long long out_ld) {
+  griddep_sync();
   const int V = n / 8;
   const long long total = rows * V;
   const long long plane = rows * p_ld;
@@ -209,11 +213,10 @@ extern "C" int ivv_splitk_reduce(const float* partial, int32_t splits, int64_t r
   IVV_REQUIRE(!rowbias || (rowbias_group > 0 && rowbias_ld % 8 == 0), "ivv_splitk_reduce: bad rowbias geometry");
   IVV_REQUIRE(!residual || res_ld % 8 == 0, "ivv_splitk_reduce: res_ld must be a multiple of 8");
   const long long total = rows * (n / 8);
-  splitk_reduce_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(
-      partial, splits, rows, (int)n, p_ld, reinterpret_cast<const __half*>(bias),
-      reinterpret_cast<const __half*>(rowbias), rowbias_group > 0 ? rowbias_group : 1, rowbias_ld,
-      reinterpret_cast<const __half*>(residual), res_ld, reinterpret_cast<__half*>(out), out_ld);
-  IVV_CHECK_CUDA(cudaGetLastError());
+  IVV_CHECK_CUDA(launch_pdl(splitk_reduce_kernel, dim3(grid_for(total, 256)), dim3(256), 0, STREAM, partial, (int)splits,
+                            rows, (int)n, p_ld, reinterpret_cast<const __half*>(bias),
+                            reinterpret_cast<const __half*>(rowbias), rowbias_group > 0 ? rowbias_group : 1, rowbias_ld,
+                            reinterpret_cast<const __half*>(residual), res_ld, reinterpret_cast<__half*>(out), out_ld));
   return 0;
 }
 
@@ -224,10 +227,9 @@ extern "C" int ivv_im2col_s2(const void* x, void* out, int64_t n_img, int64_t h,
   IVV_REQUIRE(ho == (h - 2 + pad) / 2 + 1 && wo == (w - 2 + pad) / 2 + 1,
               "ivv_im2col_s2: output size must be (h-2+pad)/2+1");
   const long long total = n_img * ho * wo * 9 * (c / 8);
-  im2col_s2_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(reinterpret_cast<const __half*>(x),
-                                                             reinterpret_cast<__half*>(out), n_img, (int)h, (int)w,
-                                                             (int)c, (int)ho, (int)wo, (int)pad);
-  IVV_CHECK_CUDA(cudaGetLastError());
+  IVV_CHECK_CUDA(launch_pdl(im2col_s2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, STREAM,
+                            reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(out), n_img, (int)h, (int)w,
+                            (int)c, (int)ho, (int)wo, (int)pad));
   return 0;
 }
 
@@ -235,10 +237,9 @@ extern "C" int ivv_upsample_nearest(const void* x, void* y, int64_t n_img, int64
                                     int64_t wo, ivv_stream_t stream_) {
   IVV_REQUIRE(x && y && n_img > 0 && c % 8 == 0, "ivv_upsample_nearest: bad arguments (c must be a multiple of 8)");
   const long long total = n_img * ho * wo * (c / 8);
-  upsample_nearest_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(reinterpret_cast<const __half*>(x),
-                                                                    reinterpret_cast<__half*>(y), n_img, (int)h, (int)w,
-                                                                    (int)c, (int)ho, (int)wo);
-  IVV_CHECK_CUDA(cudaGetLastError());
+  IVV_CHECK_CUDA(launch_pdl(upsample_nearest_kernel, dim3(grid_for(total, 256)), dim3(256), 0, STREAM,
+                            reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), n_img, (int)h, (int)w,
+                            (int)c, (int)ho, (int)wo));
   return 0;
 }
 
@@ -246,10 +247,9 @@ extern "C" int ivv_concat_channels(const void* a, int64_t ca, const void* b, int
                                    ivv_stream_t stream_) {
   IVV_REQUIRE(a && b && y && rows > 0 && ca % 8 == 0 && cb % 8 == 0, "ivv_concat_channels: bad arguments");
   const long long total = rows * ((ca + cb) / 8);
-  concat_channels_kernel<<<grid_for(total, 256), 256, 0, STREAM>>>(reinterpret_cast<const __half*>(a), (int)ca,
-                                                                   reinterpret_cast<const __half*>(b), (int)cb,
-                                                                   reinterpret_cast<__half*>(y), rows);
-  IVV_CHECK_CUDA(cudaGetLastError());
+  IVV_CHECK_CUDA(launch_pdl(concat_channels_kernel, dim3(grid_for(total, 256)), dim3(256), 0, STREAM,
+                            reinterpret_cast<const __half*>(a), (int)ca, reinterpret_cast<const __half*>(b), (int)cb,
+                            reinterpret_cast<__half*>(y), rows));
   return 0;
 }
 

@@ -137,6 +137,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  griddep_sync();  // PDL: everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -370,6 +371,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   if constexpr (CS > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  griddep_sync();  // PDL: everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
     if (lane == 0) {
@@ -751,13 +753,22 @@ static int launch_persistent_cs(const CUtensorMap& tmA, const CUtensorMap& tmB, 
   cfg.blockDim = dim3(kPersistThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CS;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CS > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CS;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = CS > 1 ? 1 : 0;
+  cfg.numAttrs = na;
   IVV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmD, tmR, kp, n_tiles, total));
   return 0;
 }
@@ -782,8 +793,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKPar
     configured = true;
   }
   dim3 grid(n_tiles, m_tiles, kp.splits);
-  gemm_tc_kernel<BN, STAGES><<<grid, kGemmThreads, smem, stream>>>(tmA, tmB, kp);
-  IVV_CHECK_CUDA(cudaGetLastError());
+  IVV_CHECK_CUDA(launch_pdl(gemm_tc_kernel<BN, STAGES>, grid, dim3(kGemmThreads), smem, stream, tmA, tmB, kp));
   return 0;
 }
 

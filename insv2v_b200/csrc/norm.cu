@@ -27,6 +27,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, GnWs ws, long long
   extern __shared__ float s_part[];  // [R][C][2]
   __shared__ float s_grp[64 * 2];
   __shared__ bool s_last;
+  griddep_sync();
   const int bg = blockIdx.y;
   const int chunks = gridDim.x;
   const long long row_begin = (long long)blockIdx.x * rows_per_cta;
@@ -121,6 +122,7 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict
                                 const __half* __restrict__ beta, const float2* __restrict__ final_,
                                 long long rows_per_bg, int C, int groups, int silu, long long rows_per_cta, int V,
                                 int R) {
+  griddep_sync();
   const int bg = blockIdx.y;
   const int vec = threadIdx.x % V;
   const int rsub = threadIdx.x / V;
@@ -176,6 +178,7 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, __half* __restric
                                  long long frames, long long pe_start) {
   // LPR lanes cooperate on one row (32/LPR rows per warp): short rows (C = 320) keep every lane busy
   constexpr int RPW = 32 / LPR;
+  griddep_sync();
   const int lane = threadIdx.x & 31;
   const int sub = lane % LPR;
   const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
@@ -262,6 +265,7 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, __half* __restric
 template <typename TIn>
 __global__ void softmax_rows_kernel(const TIn* __restrict__ x, __half* __restrict__ y, long long rows, int cols,
                                     float scale) {
+  griddep_sync();
   const long long row = blockIdx.x;
   if (row >= rows) return;
   __shared__ float s_red[32];
@@ -339,9 +343,8 @@ extern "C" int ivv_groupnorm(const void* x, void* y, const void* gamma, const vo
       IVV_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
       configured = 96 * 1024;
     }
-    gn_stats_kernel<<<grid, threads, smem, stream>>>(reinterpret_cast<const __half*>(x), ws, rows_per_bg, (int)c,
-                                                     groups, rows_per_cta, V, R, eps);
-    IVV_CHECK_CUDA(cudaGetLastError());
+    IVV_CHECK_CUDA(launch_pdl(gn_stats_kernel, grid, dim3(threads), smem, stream, reinterpret_cast<const __half*>(x),
+                              ws, rows_per_bg, (int)c, groups, rows_per_cta, V, R, eps));
   }
   {
     long long chunks2 = (148 * 8 + n_bg - 1) / n_bg;
@@ -349,11 +352,10 @@ extern "C" int ivv_groupnorm(const void* x, void* y, const void* gamma, const vo
     if (rpc < 4LL * R) rpc = 4LL * R;
     chunks2 = (rows_per_bg + rpc - 1) / rpc;
     dim3 grid((unsigned)chunks2, (unsigned)n_bg);
-    gn_apply_kernel<<<grid, threads, 0, stream>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y),
-                                                  reinterpret_cast<const __half*>(gamma),
-                                                  reinterpret_cast<const __half*>(beta), ws.final_, rows_per_bg, (int)c,
-                                                  groups, silu, rpc, V, R);
-    IVV_CHECK_CUDA(cudaGetLastError());
+    IVV_CHECK_CUDA(launch_pdl(gn_apply_kernel, grid, dim3(threads), 0, stream, reinterpret_cast<const __half*>(x),
+                              reinterpret_cast<__half*>(y), reinterpret_cast<const __half*>(gamma),
+                              reinterpret_cast<const __half*>(beta), ws.final_, rows_per_bg, (int)c, groups, (int)silu,
+                              rpc, V, R));
   }
   return 0;
 }
@@ -378,8 +380,8 @@ extern "C" int ivv_layernorm(const void* x, void* y, const void* gamma, const vo
   {                                                                                                                \
     const long long rows_per_block = (long long)warps * (32 / LPR);                                                \
     const long long blocks = (rows + rows_per_block - 1) / rows_per_block;                                         \
-    layernorm_kernel<LPR, MAXV><<<(unsigned)blocks, warps * 32, 0, stream>>>(xx, yy, g, b, rows, (int)c, eps, pe,  \
-                                                                             rows_per_frame, frames, pe_start);   \
+    IVV_CHECK_CUDA(launch_pdl(layernorm_kernel<LPR, MAXV>, dim3((unsigned)blocks), dim3(warps * 32), 0, stream,   \
+                              xx, yy, g, b, rows, (int)c, eps, pe, rows_per_frame, frames, pe_start));            \
   }
   if (V <= 8 * 5) IVV_LN_LAUNCH(8, 5)
   else if (V <= 16 * 5) IVV_LN_LAUNCH(16, 5)
@@ -396,11 +398,10 @@ extern "C" int ivv_softmax_rows(const void* x, int32_t x_is_f32, void* y, int64_
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   IVV_REQUIRE(x && y && rows > 0 && cols > 0, "ivv_softmax_rows: bad arguments");
   if (x_is_f32)
-    softmax_rows_kernel<float><<<(unsigned)rows, 256, 0, stream>>>(reinterpret_cast<const float*>(x),
-                                                                   reinterpret_cast<__half*>(y), rows, (int)cols, scale);
+    IVV_CHECK_CUDA(launch_pdl(softmax_rows_kernel<float>, dim3((unsigned)rows), dim3(256), 0, stream,
+                              reinterpret_cast<const float*>(x), reinterpret_cast<__half*>(y), rows, (int)cols, scale));
   else
-    softmax_rows_kernel<__half><<<(unsigned)rows, 256, 0, stream>>>(reinterpret_cast<const __half*>(x),
-                                                                    reinterpret_cast<__half*>(y), rows, (int)cols, scale);
-  IVV_CHECK_CUDA(cudaGetLastError());
+    IVV_CHECK_CUDA(launch_pdl(softmax_rows_kernel<__half>, dim3((unsigned)rows), dim3(256), 0, stream,
+                              reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), rows, (int)cols, scale));
   return 0;
 }

@@ -137,6 +137,7 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 __global__ void temporal_attn_mma_kernel(const __half* __restrict__ qkv, __half* __restrict__ o, int frames,
                                          long long hw, int C, int heads, int heads_per_cta, float scale) {
   extern __shared__ __align__(16) uint8_t smem_t[];
+  griddep_sync();
   __half* s = reinterpret_cast<__half*>(smem_t);
   const int d = C / heads;
   const int seg = heads_per_cta * d;
@@ -284,8 +285,8 @@ extern "C" int ivv_temporal_attention(const void* qkv, void* o, int64_t clips, i
     dim3 grid((unsigned)bp, (unsigned)(heads / hpc));
     int threads = hpc * 32;
     if (threads < 64) threads = 64;
-    temporal_attn_mma_kernel<<<grid, threads, smem, stream>>>(in, out, (int)frames, hw, (int)c, heads, hpc, scale);
-    IVV_CHECK_CUDA(cudaGetLastError());
+    IVV_CHECK_CUDA(launch_pdl(temporal_attn_mma_kernel, grid, dim3(threads), smem, stream, in, out, (int)frames, hw,
+                              (int)c, heads, hpc, scale));
     return 0;
   }
   int hpc = heads;
