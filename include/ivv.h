@@ -21,7 +21,7 @@ extern "C" {
 
 typedef void* ivv_stream_t; /* cudaStream_t */
 
-#define IVV_ABI_VERSION 1
+#define IVV_ABI_VERSION 2
 
 int ivv_abi_version(void);
 const char* ivv_last_error(void);
@@ -32,13 +32,15 @@ const char* ivv_last_error(void);
  * VAE decoder (modules/vqvae/model.py:86-136,386-408).
  *   D[pix, co] = sum_{tap, ci} A[pix + tap_offset, ci] * Wt[tap][co][ci]  (+bias[co]) (+rowbias[pix/group][co])
  *                (+residual[pix, co]);  GEGLU: D[pix, j] = (acc_h + b_h) * gelu_erf(acc_g + b_g)
- * taps = 1 (Linear / 1x1 conv; h = n_img = 1, w = rows is allowed) or 9 (3x3, stride 1, zero pad 1).               */
+ * taps = 1 (Linear / 1x1 conv; h = n_img = 1, w = rows is allowed) or 9 (3x3, stride 1, zero pad 1); with
+ * tap_h x tap_w set, any odd stride-1 "same" window (RAFT's 1x5 / 5x1 GRU convolutions, torchvision raft.py:216-229):
+ * taps = tap_h * tap_w, tap t reads pixel (y + t / tap_w - tap_h / 2, x + t % tap_w - tap_w / 2).                    */
 typedef struct {
   const void* a;      /* fp16 [n_img, h, w, a_ld] (first c channels used)                                     */
   int64_t n_img, h, w, c, a_ld;
   const void* wgt;    /* fp16 [taps][n_out][w_ld]  (w_ld >= c, multiple of 8, zero padded)                     */
   int64_t n_out, w_ld;
-  int32_t taps;       /* 1 or 9                                                                                */
+  int32_t taps;       /* 1, 9, or tap_h * tap_w                                                                 */
   int32_t geglu;      /* 1: weight rows are tile-interleaved [128 hidden | 128 gate]; output width n_out/2      */
   void* d;            /* fp16 (or fp32 when out_f32) [n_img*h*w, d_ld]                                         */
   int64_t d_ld;
@@ -50,6 +52,9 @@ typedef struct {
   int64_t rowbias_group, rowbias_ld;
   const void* residual; /* fp16 [n_img*h*w, res_ld] or NULL                                                    */
   int64_t res_ld;
+  int32_t tap_h, tap_w; /* 0, 0: taps = 1 -> 1x1, taps = 9 -> 3x3; otherwise taps must equal tap_h * tap_w (both odd) */
+  int32_t relu;         /* 1: D = max(D, 0) after bias / rowbias / residual (not with GEGLU or split-K)           */
+  int32_t reserved_;
 } ivv_gemm_args;
 int ivv_gemm(const ivv_gemm_args* args, ivv_stream_t stream);
 
@@ -136,6 +141,53 @@ int ivv_flow_noise_correction(const float* delta_ref, const float* flow_lat, flo
  * eps3: fp32 [3, n] (branches uncond | image | text+image); latent fp32 [n] updated in place.                   */
 int ivv_cfg_ddim_step(const float* eps3, float* latent, float* eps_out, int64_t n, float text_cfg, float img_cfg,
                       float alpha_prod_t, float alpha_prod_prev, ivv_stream_t stream);
+
+/* ---- RAFT optical flow -------------------------------------------------------------------
+ * The reference's RAFTFlow (misc_utils/flow_utils.py:134-189) wraps torchvision.models.optical_flow.raft_large
+ * (torchvision 0.26, models/optical_flow/raft.py; file:line below refer to it). Convolutions run on ivv_gemm; the
+ * entry points here are the remaining pieces, all channels-last.                                                  */
+/* generic im2col for the strided / 7x7 convolutions (raft.py:136-138 stem, :191 convflow1, stride-2 blocks):
+ * out[(n,oy,ox), (ky*kw+kx)*c + ci] = x[n, oy*stride+ky-pad_h, ox*stride+kx-pad_w, ci], zero outside; c % 8 == 0.   */
+int ivv_im2col(const void* x, void* out, int64_t n_img, int64_t h, int64_t w, int64_t c, int32_t kh, int32_t kw,
+               int32_t stride, int32_t pad_h, int32_t pad_w, int64_t ho, int64_t wo, ivv_stream_t stream);
+/* InstanceNorm2d (imgs_per_group = 1) / BatchNorm2d with BATCH statistics (imgs_per_group = n_img: the reference
+ * never calls .eval() on RAFTFlow, inference.py:294) of the encoders' Conv2dNormActivation (raft.py:38-59), biased
+ * variance, optional affine (gamma/beta may be NULL), optional ReLU, optional residual join
+ * y = relu(residual + y) (ResidualBlock.forward, raft.py:63-71). x, y, residual: fp16 [n_img, hw, c].             */
+int ivv_channelnorm(const void* x, void* y, const void* gamma, const void* beta, int64_t n_img, int64_t hw, int64_t c,
+                    int64_t imgs_per_group, float eps, int32_t relu, const void* residual, void* stats_ws,
+                    size_t stats_ws_bytes, ivv_stream_t stream);
+size_t ivv_channelnorm_ws_bytes(int64_t n_img, int64_t c, int64_t imgs_per_group);
+/* y = relu(a + b), fp16, n % 8 == 0: the ResidualBlock join when BatchNorm is folded (eval mode)                    */
+int ivv_add_relu(const void* a, const void* b, void* y, int64_t n, ivv_stream_t stream);
+/* images fp32 [n, 3, hs, ws] -> fp16 [n, h, w, 8] (channels 3..7 zero): TF.resize(antialias=False) when the size
+ * differs (flow_utils.py:180-182) and the OpticalFlow preset's (v - 0.5) / 0.5 (flow_utils.py:184).                */
+int ivv_raft_prep_images(const float* img, void* out, int64_t n, int64_t hs, int64_t ws, int64_t h, int64_t w,
+                         ivv_stream_t stream);
+/* F.avg_pool2d(2, 2) over the last two dims of fp32 [n, h, w] -> [n, h/2, w/2] (CorrBlock.build_pyramid :388-390)  */
+int ivv_avgpool2_f32(const float* x, float* y, int64_t n, int64_t h, int64_t w, ivv_stream_t stream);
+/* CorrBlock.index_pyramid (raft.py:393-421). pyramid[l]: fp32 [n_pairs*h*w, h>>l, w>>l] (un-normalised dot
+ * products; scale = 1/sqrt(channels) is applied here), coords fp32 [n_pairs*h*w, 2] (x, y).
+ * out fp16 [rows, out_ld], channel l*(2r+1)^2 + i*(2r+1) + j = corr_l(x/2^l + i - r, y/2^l + j - r).              */
+int ivv_corr_lookup(const float* const* pyramid, int32_t levels, const float* coords, void* out, int64_t out_ld,
+                    int64_t n_pairs, int64_t h, int64_t w, int32_t radius, float scale, ivv_stream_t stream);
+/* hidden = tanh(ctx[:, :hidden]) (fp32 master h32 + fp16 into hx[:, :hidden]); hx[:, hidden:hidden+context] =
+ * relu(ctx[:, hidden:]) (raft.py:512-514)                                                                        */
+int ivv_raft_init_state(const void* ctx, int64_t ctx_ld, float* h32, void* hx, int64_t hx_ld, int64_t rows,
+                        int32_t hidden, int32_t context, ivv_stream_t stream);
+/* ConvGRU gates (raft.py:222-229). zrq fp16 [rows, zrq_ld] = [z_pre | r_pre | ...] pre-activations:
+ * ivv_gru_gate_r: rh = sigmoid(r_pre) * h;  ivv_gru_update: h = (1 - z) h + z tanh(q_pre), z = sigmoid(z_pre).    */
+int ivv_gru_gate_r(const void* zrq, int64_t zrq_ld, const float* h32, void* rh, int64_t rows, int32_t hidden,
+                   ivv_stream_t stream);
+int ivv_gru_update(const void* zrq, int64_t zrq_ld, const void* q_pre, float* h32, void* hx, int64_t hx_ld,
+                   int64_t rows, int32_t hidden, ivv_stream_t stream);
+/* coords1 += delta[:, 0:2] (delta may be NULL) (raft.py:527); flow = coords1 - grid as fp16 into flow8 [rows, 8]
+ * (input of the motion encoder's 7x7 conv) and, if flow_slot != NULL, into flow_slot[row*ld + 0..1] (raft.py:211).  */
+int ivv_raft_update_coords(const float* delta, int64_t delta_ld, float* coords1, void* flow8, void* flow_slot,
+                           int64_t flow_slot_ld, int64_t n_pairs, int64_t h, int64_t w, ivv_stream_t stream);
+/* convex 8x upsampling (torchvision _utils.upsample_flow): mask fp16 [rows, mask_ld >= 576] -> fp32 [n, 2, 8h, 8w]  */
+int ivv_convex_upsample(const void* mask, int64_t mask_ld, const float* coords1, float* out, int64_t n_pairs,
+                        int64_t h, int64_t w, ivv_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libivv_b200.so")
-SOURCES = ["api.cu", "gemm_tc.cu", "attention_tc.cu", "norm.cu", "temporal_attn.cu", "elementwise.cu", "warp.cu"]
+SOURCES = ["api.cu", "gemm_tc.cu", "attention_tc.cu", "norm.cu", "temporal_attn.cu", "elementwise.cu", "warp.cu", "raft.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

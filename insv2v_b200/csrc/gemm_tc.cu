@@ -20,7 +20,9 @@ struct GemmKParams {
   int tiles_w, tiles_h, tiles_g;  // tiles along w, h and image groups
   int W, H, NI;                   // output extent
   int kblocks;                    // ceil(c / 64) per tap
-  int taps;                       // 1 or 9
+  int taps;                       // tap_h * tap_w
+  int tap_w, tap_h;               // window geometry (stride 1, "same" zero padding): 1x1, 3x3, 1x5, 5x1, ...
+  int relu;                       // epilogue: max(x, 0) after bias / rowbias / residual
   int n_out;                      // GEMM N (weight rows)
   int out_cols;                   // columns written (n_out, or n_out/2 for GEGLU)
   int geglu, out_f32;
@@ -148,9 +150,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int tap = (it_begin + it) / p.kblocks;
         const int kb = (it_begin + it) - tap * p.kblocks;
         int dy = 0, dx = 0;
-        if (p.taps == 9) {
-          dy = tap / 3 - 1;
-          dx = tap % 3 - 1;
+        if (p.taps > 1) {
+          dy = tap / p.tap_w - (p.tap_h >> 1);
+          dx = tap % p.tap_w - (p.tap_w >> 1);
         }
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * kStageBytes;
@@ -239,6 +241,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               load8h(p.residual + pix * p.res_ld + col, nv, r_vec, rv);
 #pragma unroll
               for (int j = 0; j < 8; ++j) v[j] += rv[j];
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
             }
             store8(dptr, p.out_f32 != 0, pix * p.d_ld + col, v, nv, d_vec);
           }
@@ -398,9 +404,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           const int tap = it / p.kblocks;
           const int kb = it - tap * p.kblocks;
           int dy = 0, dx = 0;
-          if (p.taps == 9) {
-            dy = tap / 3 - 1;
-            dx = tap % 3 - 1;
+          if (p.taps > 1) {
+            dy = tap / p.tap_w - (p.tap_h >> 1);
+            dx = tap % p.tap_w - (p.tap_w >> 1);
           }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
@@ -643,6 +649,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
               v[cc * 8 + 2 * t + 1] += f.y;
             }
           }
+          if (!GEGLU && p.relu) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) v[cc * 8 + t] = fmaxf(v[cc * 8 + t], 0.f);
+          }
           uint32_t pk[4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
@@ -803,7 +813,15 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
   using namespace ivv;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   IVV_REQUIRE(a != nullptr, "ivv_gemm: null args");
-  IVV_REQUIRE(a->taps == 1 || a->taps == 9, "ivv_gemm: taps must be 1 or 9, got %d", a->taps);
+  int tap_h = a->tap_h, tap_w = a->tap_w;
+  if (tap_h == 0 && tap_w == 0) {
+    IVV_REQUIRE(a->taps == 1 || a->taps == 9, "ivv_gemm: taps must be 1 or 9 (or tap_h x tap_w given), got %d", a->taps);
+    tap_h = tap_w = a->taps == 9 ? 3 : 1;
+  }
+  IVV_REQUIRE(tap_h > 0 && tap_w > 0 && (tap_h & 1) && (tap_w & 1) && tap_h <= 15 && tap_w <= 15 &&
+                  a->taps == tap_h * tap_w,
+              "ivv_gemm: bad tap window %d x %d for taps = %d", tap_h, tap_w, a->taps);
+  IVV_REQUIRE(!(a->relu && (a->geglu || a->splits > 1)), "ivv_gemm: relu cannot be combined with GEGLU or split-K");
   IVV_REQUIRE(a->a && a->wgt && a->d, "ivv_gemm: null tensor pointer");
   IVV_REQUIRE(a->n_img > 0 && a->h > 0 && a->w > 0 && a->c > 0 && a->n_out > 0, "ivv_gemm: empty problem");
   IVV_REQUIRE(a->a_ld % 8 == 0 && a->w_ld % 8 == 0, "ivv_gemm: a_ld (%lld) and w_ld (%lld) must be multiples of 8",
@@ -822,6 +840,9 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
   kp.NI = (int)a->n_img;
   kp.kblocks = (int)((a->c + kBlockK - 1) / kBlockK);
   kp.taps = a->taps;
+  kp.tap_w = tap_w;
+  kp.tap_h = tap_h;
+  kp.relu = a->relu;
   kp.n_out = (int)a->n_out;
   kp.geglu = a->geglu;
   kp.out_cols = a->geglu ? (int)(a->n_out / 2) : (int)a->n_out;

@@ -25,7 +25,6 @@ __host__ __device__ inline size_t gn_counter_bytes(long long n_bg) { return (siz
 __global__ void gn_stats_kernel(const __half* __restrict__ x, GnWs ws, long long rows_per_bg, int C, int groups,
                                 long long rows_per_cta, int V, int R, float eps) {
   extern __shared__ float s_part[];  // [R][C][2]
-  __shared__ float s_grp[64 * 2];
   __shared__ bool s_last;
   griddep_sync();
   const int bg = blockIdx.y;
@@ -78,8 +77,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, GnWs ws, long long
   }
   __syncthreads();
   // fixed-order in-CTA reduction: thread g sums its group's channels over all row lanes
-  if (threadIdx.x < groups) {
-    const int g = threadIdx.x;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     float a = 0.f, b = 0.f;
     for (int rr = 0; rr < R; ++rr)
       for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
@@ -97,8 +95,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, GnWs ws, long long
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (threadIdx.x < groups) {
-    const int g = threadIdx.x;
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     double a = 0.0, b = 0.0;
     for (int ch = 0; ch < chunks; ++ch) {
       const float2 pv = __ldcg(&ws.partial[((long long)bg * ws.max_chunks + ch) * groups + g]);
@@ -111,7 +108,6 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, GnWs ws, long long
     if (var < 0) var = 0;
     ws.final_[(long long)bg * groups + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
   }
-  (void)s_grp;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -120,8 +116,8 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, GnWs ws, long long
 // ------------------------------------------------------------------------------------------------
 __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y, const __half* __restrict__ gamma,
                                 const __half* __restrict__ beta, const float2* __restrict__ final_,
-                                long long rows_per_bg, int C, int groups, int silu, long long rows_per_cta, int V,
-                                int R) {
+                                long long rows_per_bg, int C, int groups, int act, long long rows_per_cta, int V,
+                                int R, const __half* __restrict__ residual) {
   griddep_sync();
   const int bg = blockIdx.y;
   const int vec = threadIdx.x % V;
@@ -133,25 +129,37 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict
   for (int j = 0; j < 8; ++j) {
     const int c = vec * 8 + j;
     const float2 mr = final_[(long long)bg * groups + c / cpg];
-    a[j] = mr.y * __half2float(gamma[c]);
-    b[j] = __half2float(beta[c]) - mr.x * a[j];
+    a[j] = mr.y * (gamma ? __half2float(gamma[c]) : 1.f);
+    b[j] = (beta ? __half2float(beta[c]) : 0.f) - mr.x * a[j];
   }
   const long long row_begin = (long long)blockIdx.x * rows_per_cta;
   const long long row_end = min(rows_per_bg, row_begin + rows_per_cta);
   const __half* xb = x + ((long long)bg * rows_per_bg) * C + vec * 8;
   __half* yb = y + ((long long)bg * rows_per_bg) * C + vec * 8;
-  auto xform = [&](const uint4& u) {
+  // act: 0 none, 1 SiLU, 2 ReLU; residual (channel norm only): y = relu(residual + act(norm(x)))
+  const __half* rbase = residual ? residual + ((long long)bg * rows_per_bg) * C + vec * 8 : nullptr;
+  auto xform = [&](const uint4& u, long long r) {
     const __half2* h = reinterpret_cast<const __half2*>(&u);
-    uint4 o;
+    uint4 o, ru = make_uint4(0, 0, 0, 0);
+    if (rbase) ru = *reinterpret_cast<const uint4*>(rbase + r * C);
+    const __half2* rh = reinterpret_cast<const __half2*>(&ru);
     __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 f = __half22float2(h[j]);
       float v0 = fmaf(f.x, a[2 * j], b[2 * j]);
       float v1 = fmaf(f.y, a[2 * j + 1], b[2 * j + 1]);
-      if (silu) {
+      if (act == 1) {
         v0 = silu_f(v0);
         v1 = silu_f(v1);
+      } else if (act == 2) {
+        v0 = fmaxf(v0, 0.f);
+        v1 = fmaxf(v1, 0.f);
+      }
+      if (rbase) {
+        const float2 rf = __half22float2(rh[j]);
+        v0 = fmaxf(v0 + rf.x, 0.f);
+        v1 = fmaxf(v1 + rf.y, 0.f);
       }
       oh[j] = __floats2half2_rn(v0, v1);
     }
@@ -163,9 +171,11 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict
 #pragma unroll
     for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(xb + (r + (long long)k * R) * C);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(yb + (r + (long long)k * R) * C) = xform(u[k]);
+    for (int k = 0; k < 4; ++k)
+      *reinterpret_cast<uint4*>(yb + (r + (long long)k * R) * C) = xform(u[k], r + (long long)k * R);
   }
-  for (; r < row_end; r += R) *reinterpret_cast<uint4*>(yb + r * C) = xform(*reinterpret_cast<const uint4*>(xb + r * C));
+  for (; r < row_end; r += R)
+    *reinterpret_cast<uint4*>(yb + r * C) = xform(*reinterpret_cast<const uint4*>(xb + r * C), r);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -301,17 +311,17 @@ extern "C" size_t ivv_groupnorm_ws_bytes(int64_t n_img, int32_t groups, int64_t 
          (size_t)n_bg * ivv::gn_max_chunks(n_bg) * groups * sizeof(float2);
 }
 
-extern "C" int ivv_groupnorm(const void* x, void* y, const void* gamma, const void* beta, int64_t n_img, int64_t hw,
-                             int64_t c, int32_t groups, int64_t frames_per_group, float eps, int32_t silu,
-                             void* stats_ws, size_t stats_ws_bytes, ivv_stream_t stream_) {
-  using namespace ivv;
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  IVV_REQUIRE(x && y && gamma && beta && stats_ws, "ivv_groupnorm: null pointer");
+namespace ivv {
+static int groupnorm_impl(const void* x, void* y, const void* gamma, const void* beta, int64_t n_img, int64_t hw,
+                          int64_t c, int32_t groups, int64_t frames_per_group, float eps, int32_t act,
+                          const void* residual, void* stats_ws, size_t stats_ws_bytes, int max_groups,
+                          cudaStream_t stream) {
+  IVV_REQUIRE(x && y && stats_ws, "ivv_groupnorm: null pointer");
   IVV_REQUIRE(n_img > 0 && hw > 0 && c > 0, "ivv_groupnorm: empty input");
   IVV_REQUIRE(frames_per_group > 0 && n_img % frames_per_group == 0,
               "ivv_groupnorm: n_img (%lld) must be a multiple of frames_per_group (%lld)", (long long)n_img,
               (long long)frames_per_group);
-  IVV_REQUIRE(groups > 0 && groups <= 64 && c % groups == 0, "ivv_groupnorm: bad groups %d for c=%lld", groups,
+  IVV_REQUIRE(groups > 0 && groups <= max_groups && c % groups == 0, "ivv_groupnorm: bad groups %d for c=%lld", groups,
               (long long)c);
   IVV_REQUIRE(c % 8 == 0 && c <= 8192, "ivv_groupnorm: c (%lld) must be a multiple of 8 and <= 8192", (long long)c);
   const size_t need = ivv_groupnorm_ws_bytes(n_img, groups, frames_per_group);
@@ -354,10 +364,33 @@ extern "C" int ivv_groupnorm(const void* x, void* y, const void* gamma, const vo
     dim3 grid((unsigned)chunks2, (unsigned)n_bg);
     IVV_CHECK_CUDA(launch_pdl(gn_apply_kernel, grid, dim3(threads), 0, stream, reinterpret_cast<const __half*>(x),
                               reinterpret_cast<__half*>(y), reinterpret_cast<const __half*>(gamma),
-                              reinterpret_cast<const __half*>(beta), ws.final_, rows_per_bg, (int)c, groups, (int)silu,
-                              rpc, V, R));
+                              reinterpret_cast<const __half*>(beta), ws.final_, rows_per_bg, (int)c, groups, (int)act,
+                              rpc, V, R, reinterpret_cast<const __half*>(residual)));
   }
   return 0;
+}
+}  // namespace ivv
+
+extern "C" int ivv_groupnorm(const void* x, void* y, const void* gamma, const void* beta, int64_t n_img, int64_t hw,
+                             int64_t c, int32_t groups, int64_t frames_per_group, float eps, int32_t silu,
+                             void* stats_ws, size_t stats_ws_bytes, ivv_stream_t stream_) {
+  IVV_REQUIRE(gamma && beta, "ivv_groupnorm: null pointer");
+  return ivv::groupnorm_impl(x, y, gamma, beta, n_img, hw, c, groups, frames_per_group, eps, silu ? 1 : 0, nullptr,
+                             stats_ws, stats_ws_bytes, 64, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+// Per-channel normalisation over imgs_per_group images: InstanceNorm2d (imgs_per_group = 1) and BatchNorm2d with
+// batch statistics (imgs_per_group = n_img; the reference never puts RAFTFlow in eval mode) of torchvision's RAFT
+// encoders, + ReLU, + the residual join relu(residual + y) of ResidualBlock.forward (raft.py:63-71).
+extern "C" size_t ivv_channelnorm_ws_bytes(int64_t n_img, int64_t c, int64_t imgs_per_group) {
+  return ivv_groupnorm_ws_bytes(n_img, (int32_t)c, imgs_per_group);
+}
+extern "C" int ivv_channelnorm(const void* x, void* y, const void* gamma, const void* beta, int64_t n_img, int64_t hw,
+                               int64_t c, int64_t imgs_per_group, float eps, int32_t relu, const void* residual,
+                               void* stats_ws, size_t stats_ws_bytes, ivv_stream_t stream_) {
+  IVV_REQUIRE(c <= 1024, "ivv_channelnorm: c (%lld) must be <= 1024", (long long)c);
+  return ivv::groupnorm_impl(x, y, gamma, beta, n_img, hw, c, (int32_t)c, imgs_per_group, eps, relu ? 2 : 0, residual,
+                             stats_ws, stats_ws_bytes, 1024, reinterpret_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int ivv_layernorm(const void* x, void* y, const void* gamma, const void* beta, int64_t rows, int64_t c,

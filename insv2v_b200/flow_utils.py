@@ -4,6 +4,7 @@ plus the fused per-step motion-compensated noise correction that replaces the 12
 import torch
 
 from . import ops
+from .raft import RAFTFlow  # noqa: F401  (drop-in for misc_utils.flow_utils.RAFTFlow, flow_utils.py:134-189)
 
 
 def _f32c(t):

@@ -22,6 +22,7 @@ class GemmArgs(ctypes.Structure):
         ("d", c_void_p), ("d_ld", c_i64), ("out_f32", c_i32), ("splits", c_i32),
         ("bias", c_void_p), ("rowbias", c_void_p), ("rowbias_group", c_i64), ("rowbias_ld", c_i64),
         ("residual", c_void_p), ("res_ld", c_i64),
+        ("tap_h", c_i32), ("tap_w", c_i32), ("relu", c_i32), ("reserved_", c_i32),
     ]
 
 
@@ -53,8 +54,26 @@ SIGNATURES = {
     "ivv_resize_flow": (c_i32, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_void_p]),
     "ivv_flow_noise_correction": (c_i32, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_void_p]),
     "ivv_cfg_ddim_step": (c_i32, [c_void_p, c_void_p, c_void_p, c_i64, c_f32, c_f32, c_f32, c_f32, c_void_p]),
+    # RAFT optical flow
+    "ivv_im2col": (c_i32, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i64,
+                           c_i64, c_void_p]),
+    "ivv_channelnorm": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_f32, c_i32,
+                                c_void_p, c_void_p, c_size, c_void_p]),
+    "ivv_channelnorm_ws_bytes": (c_size, [c_i64, c_i64, c_i64]),
+    "ivv_add_relu": (c_i32, [c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
+    "ivv_raft_prep_images": (c_i32, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_void_p]),
+    "ivv_avgpool2_f32": (c_i32, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
+    "ivv_corr_lookup": (c_i32, [ctypes.POINTER(c_void_p), c_i32, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i32,
+                                c_f32, c_void_p]),
+    "ivv_raft_init_state": (c_i32, [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_i64, c_i32, c_i32, c_void_p]),
+    "ivv_gru_gate_r": (c_i32, [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_i32, c_void_p]),
+    "ivv_gru_update": (c_i32, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i32, c_void_p]),
+    "ivv_raft_update_coords": (c_i32, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64,
+                                       c_void_p]),
+    "ivv_convex_upsample": (c_i32, [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
 }
 
+ABI_VERSION = 2  # IVV_ABI_VERSION of include/ivv.h
 _lib = None
 LAUNCH_COUNT = 0  # incremented by ops.py for every kernel-launching C-ABI call (bench.py reports it)
 
@@ -73,8 +92,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError if a declared symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.ivv_abi_version() != 1:
-        raise RuntimeError(f"libivv_b200.so ABI version {lib.ivv_abi_version()} != 1")
+    if lib.ivv_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libivv_b200.so ABI version {lib.ivv_abi_version()} != {ABI_VERSION} (stale build?)")
     _lib = lib
     return lib
 

@@ -25,6 +25,17 @@ def _chk16(t, name):
                          f"contiguous={t.is_contiguous()}")
 
 
+def _chk16v(t, name):
+    """Like _chk16 but also accepts a column-slice view of a row-major buffer (unit inner stride, 16-byte aligned)."""
+    if t is None:
+        return
+    if not t.is_cuda or t.dtype != F16 or t.stride(-1) != 1 or t.data_ptr() % 16 != 0:
+        raise ValueError(f"{name}: expected a CUDA fp16 tensor with unit inner stride and 16-byte alignment, got "
+                         f"{t.dtype} {t.device} strides={t.stride()}")
+    if t.dim() != 2 and not t.is_contiguous():
+        raise ValueError(f"{name}: only 2-D tensors may be strided views")
+
+
 def _count():
     _lib.LAUNCH_COUNT += 1
 
@@ -130,18 +141,23 @@ def _splitk_policy(rows, k_total, n_out):
 
 
 def gemm(a, wgt, *, n_img, h, w, c, n_out=None, taps=1, a_ld=None, bias=None, rowbias=None, rowbias_group=0,
-         residual=None, geglu=False, out=None, out_f32=False, _splits=1):
-    """D = conv/linear(A, W) with fused epilogue; A rows are pixels [n_img*h*w, a_ld], W packed by pack_*()."""
-    _chk16(a, "a"), _chk16(wgt, "wgt"), _chk16(bias, "bias"), _chk16(rowbias, "rowbias"), _chk16(residual, "residual")
+         residual=None, geglu=False, out=None, out_f32=False, _splits=1, tap_hw=None, relu=False):
+    """D = conv/linear(A, W) with fused epilogue; A rows are pixels [n_img*h*w, a_ld], W packed by pack_*().
+    a / out / residual may be column-slice views of wider row-major buffers (their row stride is passed as the
+    leading dimension). tap_hw = (kh, kw): odd stride-1 'same' window other than 1x1 / 3x3 (taps = kh*kw)."""
+    _chk16v(a, "a"), _chk16(wgt, "wgt"), _chk16(bias, "bias"), _chk16(rowbias, "rowbias"), _chk16v(residual, "residual")
     if wgt.dim() != 3 or wgt.shape[0] != taps:
         raise ValueError(f"weight must be [taps={taps}, n_out, k_pad], got {tuple(wgt.shape)}")
     n_out = wgt.shape[1] if n_out is None else n_out
-    a_ld = a.shape[-1] if a_ld is None else a_ld
+    a_ld = a.stride(-2) if a_ld is None else a_ld
     rows = n_img * h * w
     cols = n_out // 2 if geglu else n_out
     # split-K for the few-row / long-K convolutions of the 4x6 and 8x12 levels: too few output tiles for 148 SMs
-    splits = _splitk_policy(rows, c * taps, n_out) if (SPLITK and not geglu and not out_f32 and
-                                                        (out is None or out.dtype == F16)) else 1
+    splits = _splitk_policy(rows, c * taps, n_out) if (SPLITK and not geglu and not out_f32 and not relu and
+                                                        tap_hw is None and a.is_contiguous() and
+                                                        (residual is None or residual.is_contiguous()) and
+                                                        (out is None or (out.dtype == F16 and out.is_contiguous()))
+                                                        ) else 1
     if splits > 1:
         partial = empty((splits, rows, n_out), torch.float32, a.device)
         gemm(a, wgt, n_img=n_img, h=h, w=w, c=c, n_out=n_out, taps=taps, a_ld=a_ld, out=partial, _splits=splits)
@@ -159,13 +175,18 @@ def gemm(a, wgt, *, n_img, h, w, c, n_out=None, taps=1, a_ld=None, bias=None, ro
     args.a, args.n_img, args.h, args.w, args.c, args.a_ld = a.data_ptr(), n_img, h, w, c, a_ld
     args.wgt, args.n_out, args.w_ld = wgt.data_ptr(), n_out, wgt.shape[2]
     args.taps, args.geglu = taps, int(geglu)
-    args.d, args.d_ld, args.out_f32 = out.data_ptr(), out.shape[-1], int(out.dtype == torch.float32)
+    if out.stride(-1) != 1:
+        raise ValueError("gemm: out must have unit inner stride")
+    args.d, args.d_ld, args.out_f32 = out.data_ptr(), out.stride(-2), int(out.dtype == torch.float32)
     args.splits = _splits
+    args.relu = int(relu)
+    if tap_hw is not None:
+        args.tap_h, args.tap_w = tap_hw
     args.bias = bias.data_ptr() if bias is not None else None
     if rowbias is not None:
         args.rowbias, args.rowbias_group, args.rowbias_ld = rowbias.data_ptr(), rowbias_group, rowbias.shape[-1]
     if residual is not None:
-        args.residual, args.res_ld = residual.data_ptr(), residual.shape[-1]
+        args.residual, args.res_ld = residual.data_ptr(), residual.stride(-2)
     e0 = Prof.begin()
     _lib.check(_lib.load().ivv_gemm(ctypes.byref(args), _s()), "ivv_gemm")
     if e0 is not None:
@@ -292,6 +313,52 @@ def softmax_rows(x, scale, out=None):
                                             _s()), "ivv_softmax_rows")
     _count()
     return out
+
+
+def channelnorm(x, n_img, hw, imgs_per_group, gamma=None, beta=None, eps=1e-5, relu=False, residual=None, out=None):
+    """InstanceNorm2d (imgs_per_group=1) / batch-statistics BatchNorm2d (imgs_per_group=n_img) over frames
+    [n_img*hw, c], + ReLU, + relu(residual + y) (torchvision raft.py ResidualBlock)."""
+    _chk16(x, "x"), _chk16(gamma, "gamma"), _chk16(beta, "beta"), _chk16(residual, "residual")
+    c = x.shape[-1]
+    if out is None:
+        out = empty(x.shape, F16, x.device)
+    L = _lib.load()
+    ws = _gn_ws(L.ivv_channelnorm_ws_bytes(n_img, c, imgs_per_group), x.device)
+    _lib.check(L.ivv_channelnorm(_p(x), _p(out), _p(gamma), _p(beta), n_img, hw, c, imgs_per_group, float(eps),
+                                 int(relu), _p(residual), _p(ws), ws.numel(), _s()), "ivv_channelnorm")
+    _lib.LAUNCH_COUNT += 2
+    return out
+
+
+def im2col(x, n_img, h, w, kh, kw, stride, pad_h, pad_w):
+    """frames [n_img*h*w, c] -> [n_img*ho*wo, kh*kw*c] (column = tap*c + ci), zero padded."""
+    _chk16(x, "x")
+    c = x.shape[-1]
+    ho, wo = (h + 2 * pad_h - kh) // stride + 1, (w + 2 * pad_w - kw) // stride + 1
+    out = empty((n_img * ho * wo, kh * kw * c), F16, x.device)
+    _lib.check(_lib.load().ivv_im2col(_p(x), _p(out), n_img, h, w, c, kh, kw, stride, pad_h, pad_w, ho, wo, _s()),
+               "ivv_im2col")
+    _count()
+    return out, ho, wo
+
+
+def pack_conv_im2col(w, c_pad=None):
+    """Conv2d weight [co, ci, kh, kw] -> fp16 [1, co, kh*kw*c_pad] in ivv_im2col's column order (tap*c_pad + ci)."""
+    co, ci, kh, kw = w.shape
+    c_pad = ci if c_pad is None else c_pad
+    t = w.new_zeros(co, kh, kw, c_pad)
+    t[..., :ci] = w.permute(0, 2, 3, 1)
+    return t.to(F16).reshape(1, co, kh * kw * c_pad).contiguous()
+
+
+def pack_conv_taps(w, c_pad=None, co_pad=None):
+    """Conv2d weight [co, ci, kh, kw] -> fp16 [kh*kw, co_pad, c_pad8] (tap = ky*kw + kx) for the implicit-tap GEMM."""
+    co, ci, kh, kw = w.shape
+    c_pad = (ci + 7) // 8 * 8 if c_pad is None else c_pad
+    co_pad = co if co_pad is None else co_pad
+    t = w.new_zeros(kh * kw, co_pad, c_pad)
+    t[:, :co, :ci] = w.permute(2, 3, 0, 1).reshape(kh * kw, co, ci)
+    return t.to(F16).contiguous()
 
 
 # ----------------------------------------------------------------------------------------------------------------

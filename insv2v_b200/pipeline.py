@@ -26,20 +26,37 @@ def ddim_timesteps(num_steps, n_train=1000, steps_offset=1):
 
 
 class InsV2VPipeline:
-    def __init__(self, unet, vae=None, num_ddim_steps=20, scale_factor=0.18215, beta_start=0.00085, beta_end=0.012):
+    def __init__(self, unet, vae=None, num_ddim_steps=20, scale_factor=0.18215, beta_start=0.00085, beta_end=0.012,
+                 flow_estimator=None):
         self.unet, self.vae = unet, vae
+        self.flow_estimator = flow_estimator  # insv2v_b200.raft.RAFTFlow (InferenceIP2PVideoOpticalFlow, inference.py:294)
         self.num_ddim_steps = num_ddim_steps
         self.scale_factor = scale_factor
         self.ac = alphas_cumprod(beta_start, beta_end).tolist()
         self.timesteps = ddim_timesteps(num_ddim_steps)
 
     @torch.no_grad()
+    def obtain_flows(self, ref_images, query_images):
+        """obtain_flow_batched (inference.py:303-311): for every query frame, the RAFT flow from the query (repeated
+        over the batch) to each of the R reference frames. ref_images [R, 3, H, W], query_images [Q, 3, H, W] in
+        [0, 1]. Returns Q tensors [R, 2, H, W] - the `flows=` argument of denoise()."""
+        if self.flow_estimator is None:
+            raise RuntimeError("no flow_estimator: build the pipeline with flow_estimator=insv2v_b200.raft.RAFTFlow(...)")
+        r = ref_images.shape[0]
+        return [self.flow_estimator(q.unsqueeze(0).repeat(r, 1, 1, 1), ref_images) for q in query_images]
+
+    @torch.no_grad()
     def denoise(self, latent, text_cond, text_uncond, img_cond, text_cfg=7.5, img_cfg=1.2, latent_ref=None,
-                noise_correct_step=1.0, flows=None):
+                noise_correct_step=1.0, flows=None, ref_images=None, query_images=None):
         """latent, img_cond [1, F, 4, h, w]; text_* [1, 77, C]; latent_ref [1, R, 4, h, w] (chained clips);
-        flows: list of Q tensors [R, 2, H, W] at pixel resolution (optical-flow variant). Returns the final latent."""
+        flows: list of Q tensors [R, 2, H, W] at pixel resolution (optical-flow variant), or ref_images
+        [1, R, 3, H, W] + query_images [1, Q, 3, H, W] as in second_clip_forward (inference.py:313-345), from which
+        the flows are estimated with RAFT first. Returns the final latent."""
         if latent.shape[0] != 1:
             raise ValueError("one clip per call (shard clips across GPUs with insv2v_b200.parallel)")
+        if flows is None and ref_images is not None:
+            assert ref_images.shape[0] == 1, 'only support batch size 1'
+            flows = self.obtain_flows(ref_images[0], query_images[0])
         dev = latent.device
         _, f, c, h, w = latent.shape
         n = latent.numel()

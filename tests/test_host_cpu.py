@@ -98,7 +98,7 @@ def test_library_exports_every_declared_symbol():
     L = lib.load()
     for name in declared:
         assert hasattr(L, name)
-    assert L.ivv_abi_version() == 1
+    assert L.ivv_abi_version() == 2
     assert L.ivv_groupnorm_ws_bytes(48, 32, 16) >= 3 * 32 * 2 * 8 and L.ivv_groupnorm_ws_bytes(48, 32, 0) == 0
 
 
@@ -172,3 +172,19 @@ def test_clip_parallel_world_size_2_gloo(tmp_path, n_clips):
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "[rank0-ok]" in r.stdout and "[rank1-ok]" in r.stdout
+
+
+def test_raftflow_parameter_tree_is_torchvisions():
+    """RAFTFlow drop-in (misc_utils/flow_utils.py:134-189): `model.*` keys and shapes of torchvision raft_large, CPU
+    tensors are refused (no CPU path), weights load from a raft_large state dict."""
+    import pytest
+    from torchvision.models.optical_flow import raft_large
+    from insv2v_b200.raft import RAFTFlow
+    tv = raft_large(weights=None)
+    m = RAFTFlow(weights=tv.state_dict())
+    got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert got == {"model." + k: tuple(v.shape) for k, v in tv.state_dict().items()}
+    assert torch.equal(m.model.update_block.flow_head.conv2.weight, tv.update_block.flow_head.conv2.weight)
+    assert m.training  # the reference never calls .eval() (inference.py:294)
+    with pytest.raises(RuntimeError, match="only on CUDA"):
+        m(torch.zeros(1, 3, 128, 128), torch.zeros(1, 3, 128, 128))

@@ -87,3 +87,36 @@ def test_ddim_schedule_matches_reference():
     from insv2v_b200 import pipeline as P
     assert P.ddim_timesteps(50) == meta["ddim_timesteps_50"]
     assert torch.equal(P.alphas_cumprod(), O.alphas_cumprod())
+
+
+# ------------------------------------------------------------------------------------------------ RAFT optical flow
+def test_raft_oracle_is_pinned_to_torchvision_raft_large():
+    """The reference's RAFTFlow wraps torchvision.models.optical_flow.raft_large (misc_utils/flow_utils.py:155-159);
+    the restatement in oracle/raft_oracle.py must reproduce that module bit for bit, in the mode the reference runs it
+    (train: batch-statistics BatchNorm) and in eval mode, and its schema must be the module's state dict."""
+    from torchvision.models.optical_flow import raft_large
+    from oracle import raft_oracle as R
+    sd = R.raft_seeded_state_dict(5)
+    tv = raft_large(weights=None)
+    assert {k: tuple(v.shape) for k, v in tv.state_dict().items()} == R.raft_schema()
+    tv.load_state_dict(sd)
+    g = torch.Generator().manual_seed(6)
+    img1, img2 = torch.rand(1, 3, 128, 128, generator=g) * 2 - 1, torch.rand(1, 3, 128, 128, generator=g) * 2 - 1
+    with torch.no_grad():
+        for training in (True, False):
+            tv.train(training)
+            ref = tv(img1, img2, num_flow_updates=4)
+            tv.load_state_dict(sd)  # train-mode forward updates the running statistics
+            mine = R.raft_forward(sd, img1, img2, num_flow_updates=4, bn_training=training, return_all=True)
+            assert len(ref) == len(mine) == 4
+            for a, b in zip(ref, mine):
+                assert torch.equal(a, b)
+
+
+def test_raft_golden_is_the_oracles_output():
+    from oracle import raft_oracle as R
+    g = golden("raft_small.pt")
+    sd = R.raft_seeded_state_dict(g["seed_w"])
+    with torch.no_grad():
+        flow = R.raft_flow(sd, g["img1"].float() / 255, g["img2"].float() / 255)
+    _close(flow, g["flow"], 1e-5)
