@@ -184,7 +184,7 @@ class _Engine:
         return u
 
     # ---- conv -> norm -> relu (-> residual join) -----------------------------------------------------------------
-    def _cna(self, a, u, n, h, w, relu, residual=None, **gemm_geom):
+    def _cna(self, a, u, n_imgs, hw, relu, residual=None, **gemm_geom):
         L = _lib.load()
         folded = u.norm == "folded"
         y = ops.gemm(a, u.w, bias=u.b, relu=folded and relu, **gemm_geom)
@@ -193,23 +193,24 @@ class _Engine:
                 _lib.check(L.ivv_add_relu(ops._p(y), ops._p(residual), ops._p(y), y.numel(), ops._s()), "ivv_add_relu")
                 ops._count()
             return y
-        return ops.channelnorm(y, n, h * w, n if u.norm == "batch" else 1, u.gamma, u.beta, 1e-5, relu, residual, out=y)
+        return ops.channelnorm(y, n_imgs, hw, n_imgs if u.norm == "batch" else 1, u.gamma, u.beta, 1e-5, relu, residual,
+                               out=y)
 
     def _encoder(self, x, n, H, W, E):
         cols, h, w = ops.im2col(x, n, H, W, 7, 7, 2, 3, 3)
-        y = self._cna(cols, E["stem"], n, h, w, True, n_img=1, h=1, w=n * h * w, c=cols.shape[1])
+        y = self._cna(cols, E["stem"], n, h * w, True, n_img=1, h=1, w=n * h * w, c=cols.shape[1])
         for blk in E["blocks"]:
             if blk["s2"]:
                 c = y.shape[1]
                 cols, h, w = ops.im2col(y, n, h, w, 3, 3, 2, 1, 1)
                 rows = n * h * w
-                t = self._cna(cols, blk["c1"], n, h, w, True, n_img=1, h=1, w=rows, c=9 * c)
+                t = self._cna(cols, blk["c1"], n, h * w, True, n_img=1, h=1, w=rows, c=9 * c)
                 # the 1x1 stride-2 projection reads the centre tap of the same im2col matrix
-                skip = self._cna(cols[:, 4 * c:5 * c], blk["ds"], n, h, w, False, n_img=1, h=1, w=rows, c=c)
+                skip = self._cna(cols[:, 4 * c:5 * c], blk["ds"], n, h * w, False, n_img=1, h=1, w=rows, c=c)
             else:
-                t = self._cna(y, blk["c1"], n, h, w, True, n_img=n, h=h, w=w, c=y.shape[1], taps=9)
+                t = self._cna(y, blk["c1"], n, h * w, True, n_img=n, h=h, w=w, c=y.shape[1], taps=9)
                 skip = y
-            y = self._cna(t, blk["c2"], n, h, w, True, residual=skip, n_img=n, h=h, w=w, c=t.shape[1], taps=9)
+            y = self._cna(t, blk["c2"], n, h * w, True, residual=skip, n_img=n, h=h, w=w, c=t.shape[1], taps=9)
         return ops.linear(y, E["conv"][0], bias=E["conv"][1]), h, w
 
     # ---- the whole estimator ---------------------------------------------------------------------------------------

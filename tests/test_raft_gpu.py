@@ -48,7 +48,7 @@ def nchw(fr, n, h, w):
 
 
 def report(name, got, ref, rtol=RTOL, atol=ATOL):
-    got, ref = got.float(), ref.float()
+    got, ref = got.float().cpu(), ref.float().cpu()
     err = (got - ref).abs()
     bad = (err > atol + rtol * ref.abs()).float().mean().item()
     print(f"[{name}] max_abs={err.max().item():.3e} max_ref={ref.abs().max().item():.3e} viol_frac={bad:.3e}")
@@ -224,6 +224,30 @@ def _model(seed, train=True):
     from insv2v_b200.raft import RAFTFlow
     m = RAFTFlow(weights=_oracle().raft_seeded_state_dict(seed)).to(DEV)
     return m.train(train)
+
+
+def test_raft_encoders_match_oracle():
+    """Feature (InstanceNorm) and context (batch-statistics BatchNorm) encoders on the golden inputs: 13 fp16
+    convolution + norm layers against the fp32 oracle, 0.5 % of the feature maps' L2 norm."""
+    from insv2v_b200.raft import _Engine
+    ro, L, ops = _oracle(), _lib().load(), _ops()
+    g = golden("raft_small.pt")
+    sd = ro.raft_seeded_state_dict(g["seed_w"])
+    m = _model(g["seed_w"])
+    eng = _Engine(m.model, torch.device(DEV, torch.cuda.current_device()), True)
+    imgs = torch.cat([g["img1"], g["img2"]]).float().div(255)
+    n, _, H, W = imgs.shape
+    x = torch.empty(n * H * W, 8, device=DEV, dtype=torch.float16)
+    _lib().check(L.ivv_raft_prep_images(ops._p(imgs.to(DEV).contiguous()), ops._p(x), n, H, W, H, W, ops._s()), "prep")
+    ref_in = (imgs - 0.5) / 0.5
+    report("prep", nchw(x[:, :3], n, H, W), ref_in)
+    for enc, batch, nimg in (("feature_encoder", False, n), ("context_encoder", True, n // 2)):
+        fm, h, w = eng._encoder(x[:nimg * H * W], nimg, H, W, eng.enc[enc])
+        with torch.no_grad():
+            ref = ro.feature_encoder(sd, enc, ref_in[:nimg], batch, True)
+        st = err_stats(nchw(fm, nimg, h, w), ref)
+        print(f"[raft {enc}]", st)
+        assert (h, w) == (H // 8, W // 8) and st["rel_l2"] < 5e-3
 
 
 def test_raft_golden_flow():
