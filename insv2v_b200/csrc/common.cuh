@@ -81,6 +81,21 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Entry into a single-thread role (TMA producer, MMA issuer) from a converged warp. elect.sync lets ptxas prove that one
+// thread runs the branch, so descriptors and barrier addresses live in uniform registers and tcgen05.mma / TMA issue
+// back to back; with `lane == 0` each of them sits in an ELECT + R2UR + BRA.U.ANY loop. -DIVV_ROLE_ELECT=0 restores the
+// old form for A/B timing (tools/gpu_ab_lib.sh).
+#ifndef IVV_ROLE_ELECT
+#define IVV_ROLE_ELECT 1
+#endif
+__device__ __forceinline__ bool role_elect() {
+#if IVV_ROLE_ELECT
+  return elect_one();
+#else
+  return (threadIdx.x & 31) == 0;
+#endif
+}
+
 // ---- mbarrier ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -141,8 +141,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_ptr;
   griddep_sync();  // PDL: everything above overlapped the previous kernel's tail
 
+  // Single-thread roles are entered through elect.sync on a converged warp, not `lane == 0`: ptxas then knows exactly
+  // one thread runs the branch and keeps descriptors / barrier addresses in uniform registers. With a divergent
+  // `lane == 0` every tcgen05.mma / TMA / commit was wrapped in an ELECT + 5x R2UR + BRA.U.ANY serialisation loop
+  // (~15 scalar instructions per MMA), which paced the main loop instead of the tensor pipe.
   if (warp == 0) {
-    if (lane == 0) {
+    if (role_elect()) {
       // ===== TMA producer =====
       int stage = 0;
       uint32_t phase = 0;
@@ -167,7 +171,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (role_elect()) {
       // ===== MMA issuer =====
       constexpr uint32_t idesc = umma_idesc_f16(kBlockM, BN, 0, 0);
       int stage = 0;
@@ -380,7 +384,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   griddep_sync();  // PDL: everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (role_elect()) {  // elect.sync, not lane == 0: see gemm_tc_kernel
       // ===== TMA producer =====
       int stage = 0;
       uint32_t phase = 0;
@@ -455,7 +459,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && (!TWO || crank == 0)) {
+    if ((!TWO || crank == 0) && role_elect()) {
       // ===== MMA issuer (pair mode: the leader CTA issues for both) =====
       constexpr uint32_t idesc = umma_idesc_f16(TWO ? 2 * kBlockM : kBlockM, BN, 0, 0);
       int stage = 0;

@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libivv_b200.so")
+LIB_PATH = os.environ.get("IVV_LIB_PATH") or os.path.join(_HERE, "libivv_b200.so")  # override: tuning A/B only
 
 c_void_p = ctypes.c_void_p
 c_i64 = ctypes.c_int64

@@ -206,6 +206,22 @@ def test_self_attention(n, s, heads, d):
     report(f"self-attn n{n} s{s} h{heads} d{d}", out.reshape(n, s, c), ref, rtol=2e-3, atol=5e-4)
 
 
+@pytest.mark.parametrize("s_q,s_kv,d,gain", [(1536, 1536, 40, 3.0), (640, 900, 40, 4.0), (300, 1100, 24, 2.0),
+                                             (256, 257, 56, 1.0), (384, 384, 80, 3.0)])
+def test_self_attention_peaky(s_q, s_kv, d, gain):
+    """Large score ranges (|q.k|*scale up to ~50): the running maximum jumps, so the lazy O rescale, the masked last
+    block, the ghost tile of an odd CTA pair and the FMA-pipe exp2 (arguments down to -125) are all exercised."""
+    ops = _ops()
+    n, heads = 2, 4
+    c = heads * d
+    q = h16(n * s_q, c, scale=gain, seed=1)
+    kv = h16(n * s_kv, 2 * c, scale=gain, seed=2)
+    out = ops.attention(q, kv[:, :c], kv[:, c:], n_batch=n, s_q=s_q, s_kv=s_kv, heads=heads, d=d, q_ld=c, kv_ld=2 * c)
+    k, v = (t.float().reshape(n, s_kv, c) for t in kv.chunk(2, dim=-1))
+    ref = _sdpa_ref(q.float().reshape(n, s_q, c), k, v, heads)
+    report(f"peaky self-attn sq{s_q} skv{s_kv} d{d}", out.reshape(n, s_q, c), ref, rtol=2e-3, atol=5e-4 * gain)
+
+
 @pytest.mark.parametrize("clips,frames,s,heads,d", [(3, 4, 384, 8, 80), (2, 3, 1536, 8, 40), (2, 2, 24, 8, 160)])
 def test_cross_attention(clips, frames, s, heads, d):
     ops = _ops()
@@ -372,7 +388,11 @@ print("variant ok")
 """
 
 
-@pytest.mark.parametrize("env", [{"IVV_PAIR": "0"}, {"IVV_PAIR": "0", "IVV_CLUSTER": "2"}, {"IVV_ATTN_TWO_TILE": "1"},
+@pytest.mark.parametrize("env", [{"IVV_PAIR": "0"}, {"IVV_PAIR": "0", "IVV_CLUSTER": "2"},
+                                 {"IVV_ATTN_PAIR": "0", "IVV_ATTN_TWO_TILE": "1"}, {"IVV_ATTN_PAIR": "0"},
+                                 {"IVV_ATTN_PAIR": "0", "IVV_ATTN_QK_FIRST": "0"}, {"IVV_ATTN_MODE": "0"},
+                                 {"IVV_ATTN_MODE": "1"}, {"IVV_ATTN_MODE": "2"}, {"IVV_ATTN_POLY": "1"},
+                                 {"IVV_ATTN_MODE": "0", "IVV_ATTN_POLY": "1"},
                                  {"IVV_FORCE_BN": "128"}, {"IVV_FORCE_BN": "256"}])
 def test_kernel_variants(env):
     """The opt-in / fallback code paths (single-CTA GEMM, multicast clusters, two-tile attention, other tile widths)
