@@ -206,15 +206,10 @@ __device__ __forceinline__ void softmax_tile(const AttnParams& p, int r, uint32_
   mbar_wait(pv_done, (nblk - 1) & 1);
   tc_fence_after();
   float inv_l;
-  {
-    uint32_t o[16];
-    tmem_ld16(tmem_O + lane_off + (p.d & ~15), o);
+  {  // the denominator is the accumulator column d (one-column load: no register array to index at run time)
+    const uint32_t lbits = tmem_ld1(tmem_O + lane_off + p.d);
     tmem_ld_wait();
-    float l = 1.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (i == (p.d & 15)) l = __uint_as_float(o[i]);
-    inv_l = 1.f / l;
+    inv_l = 1.f / __uint_as_float(lbits);
   }
   const int row = q0 + r;
   __half* orow = p.o + (static_cast<long long>(nb) * p.s_q + row) * p.o_ld + static_cast<long long>(head) * p.d;
@@ -237,7 +232,8 @@ __device__ __forceinline__ void softmax_tile(const AttnParams& p, int r, uint32_
           }
           *reinterpret_cast<uint4*>(orow + col) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         } else {
-          for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int i = 0; i < 8; ++i)  // unrolled: a runtime index would move o[] to local memory
             if (col + i < p.d) orow[col + i] = __float2half_rn(__uint_as_float(o[g * 8 + i]) * inv_l);
         }
       }
@@ -412,15 +408,10 @@ __device__ __forceinline__ void softmax_tile_sp(const AttnParams& p, int r, uint
   mbar_wait(pv_done, (nblk - 1) & 1);
   tc_fence_after();
   float inv_l;
-  {
-    uint32_t o[16];
-    tmem_ld16(tmem_O + lane_off + (p.d & ~15), o);
+  {  // the denominator is the accumulator column d (one-column load: no register array to index at run time)
+    const uint32_t lbits = tmem_ld1(tmem_O + lane_off + p.d);
     tmem_ld_wait();
-    float l = 1.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (i == (p.d & 15)) l = __uint_as_float(o[i]);
-    inv_l = 1.f / l;
+    inv_l = 1.f / __uint_as_float(lbits);
   }
   const int row = q0 + r;
   __half* orow = p.o + (static_cast<long long>(nb) * p.s_q + row) * p.o_ld + static_cast<long long>(head) * p.d;
@@ -443,7 +434,8 @@ __device__ __forceinline__ void softmax_tile_sp(const AttnParams& p, int r, uint
           }
           *reinterpret_cast<uint4*>(orow + col) = make_uint4(q4[0], q4[1], q4[2], q4[3]);
         } else {
-          for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int i = 0; i < 8; ++i)  // unrolled: a runtime index would move o[] to local memory
             if (col + i < p.d) orow[col + i] = __float2half_rn(__uint_as_float(o[g * 8 + i]) * inv_l);
         }
       }
@@ -605,15 +597,10 @@ __device__ __forceinline__ void softmax_tile_sp2(const AttnParams& p, int warp, 
   mbar_wait(pv_done, (nblk - 1) & 1);
   tc_fence_after();
   float inv_l;
-  {
-    uint32_t o[16];
-    tmem_ld16(tmem_O + lane_off + (p.d & ~15), o);
+  {  // the denominator is the accumulator column d (one-column load: no register array to index at run time)
+    const uint32_t lbits = tmem_ld1(tmem_O + lane_off + p.d);
     tmem_ld_wait();
-    float l = 1.f;
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (i == (p.d & 15)) l = __uint_as_float(o[i]);
-    inv_l = 1.f / l;
+    inv_l = 1.f / __uint_as_float(lbits);
   }
   const int row = q0 + r;
   __half* orow = p.o + (static_cast<long long>(nb) * p.s_q + row) * p.o_ld + static_cast<long long>(head) * p.d;
@@ -636,7 +623,8 @@ __device__ __forceinline__ void softmax_tile_sp2(const AttnParams& p, int warp, 
           }
           *reinterpret_cast<uint4*>(orow + col) = make_uint4(q4[0], q4[1], q4[2], q4[3]);
         } else {
-          for (int i = 0; i < 8; ++i)
+#pragma unroll
+          for (int i = 0; i < 8; ++i)  // unrolled: a runtime index would move o[] to local memory
             if (col + i < p.d) orow[col + i] = __float2half_rn(__uint_as_float(o[g * 8 + i]) * inv_l);
         }
       }
@@ -1170,8 +1158,8 @@ constexpr int attnpp_smem_bytes() {
 template <int NS, int POLY>
 __global__ void __launch_bounds__(kAttnThreads, attnpp_smem_bytes<NS>() <= 113 * 1024 ? 2 : 1)
 attention_pair_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                              const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p,
-                              const __grid_constant__ AttnPersist pp) {
+                              const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO,
+                              const __grid_constant__ AttnParams p, const __grid_constant__ AttnPersist pp) {
   constexpr uint16_t kMask = 3;
   constexpr int SW = 4;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -1207,6 +1195,7 @@ attention_pair_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __g
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&tmO);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&q_full[b], 1);
       mbar_init(&q_empty[b], 1);
@@ -1350,6 +1339,7 @@ attention_pair_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __g
     const int one_col = p.d & 31, one_chunk = one_col >> 3, one_elem = p.d & 7;
     const bool write_ones = (p.d >> 5) == crank;
     const bool lane0 = lane == 0;
+    const bool store_issuer = role_elect();  // one lane per warp; only warp 0's issues the output stores
     int st = 0;
     int g = 0;  // flat block counter
     int it = 0;
@@ -1373,8 +1363,10 @@ attention_pair_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __g
       }
       return fmaxf(mx, fmaxf(fmaxf(a, b), fmaxf(c, d)));
     };
+    // item coordinates are advanced incrementally (three runtime div/mod per item cost ~1 000 clk on this path)
+    int qp = first % pp.n_qpairs, head = (first / pp.n_qpairs) % pp.heads, nb = first / (pp.n_qpairs * pp.heads);
+    const int d_qp = step % pp.n_qpairs, d_head = (step / pp.n_qpairs) % pp.heads, d_nb = step / (pp.n_qpairs * pp.heads);
     for (int item = first; item < pp.n_items; item += step, ++it) {
-      const int qp = item % pp.n_qpairs, head = (item / pp.n_qpairs) % pp.heads, nb = item / (pp.n_qpairs * pp.heads);
       const int q0 = (2 * qp + crank) * kQ;
       const uint32_t tO = tmem_O + (it & 1) * 64 + lane_off;
       float m_run = -INFINITY;
@@ -1416,34 +1408,58 @@ attention_pair_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __g
         }
         if (redo) {
           // ---- two-pass: first block of an item, masked last block, or a row maximum that jumped ----
-          const int nchunk = (valid + 31) / 32;
-          float mx = -INFINITY;
-          for (int c = 0; c < nchunk; ++c) {
-            uint32_t v[32];
-            tmem_ld32(tmem_S + lane_off + c * 32, v);
-            tmem_ld_wait();
+          if (valid == kKV) {
+            // full block: two loads in flight per wait
+            float mx = -INFINITY;
+            uint32_t va[32], vb[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
-          }
-          if ((mx - m_run) * sl > 2.f) m_new = mx;  // also taken on the first block (m_run = -inf)
-          const float m_sl = m_new * sl;
+            for (int c = 0; c < 4; c += 2) {
+              tmem_ld32(tmem_S + lane_off + c * 32, va);
+              tmem_ld32(tmem_S + lane_off + c * 32 + 32, vb);
+              tmem_ld_wait();
+              mx = max_chunk(va, mx);
+              mx = max_chunk(vb, mx);
+            }
+            if ((mx - m_run) * sl > 2.f) m_new = mx;  // also taken on the first block (m_run = -inf)
+            const float m_sl = m_new * sl;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            if (c < nchunk) {
+            for (int c = 0; c < 4; c += 2) {
+              tmem_ld32(tmem_S + lane_off + c * 32, va);
+              tmem_ld32(tmem_S + lane_off + c * 32 + 32, vb);
+              tmem_ld_wait();
+              exp_chunk(va, c, m_sl);
+              exp_chunk(vb, c + 1, m_sl);
+            }
+          } else {
+            const int nchunk = (valid + 31) / 32;
+            float mx = -INFINITY;
+            for (int c = 0; c < nchunk; ++c) {
               uint32_t v[32];
               tmem_ld32(tmem_S + lane_off + c * 32, v);
               tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const int k0 = c * 32 + 2 * i;
-                const float x0 = (k0 < valid) ? fmaf(__uint_as_float(v[2 * i]), sl, -m_sl) : -INFINITY;
-                const float x1 = (k0 + 1 < valid) ? fmaf(__uint_as_float(v[2 * i + 1]), sl, -m_sl) : -INFINITY;
-                pk[c * 16 + i] = ex2_h2(x0, x1);
-              }
-            } else {
+              for (int i = 0; i < 32; ++i)
+                if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+            }
+            if ((mx - m_run) * sl > 2.f) m_new = mx;
+            const float m_sl = m_new * sl;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) pk[c * 16 + i] = 0u;
+            for (int c = 0; c < 4; ++c) {
+              if (c < nchunk) {
+                uint32_t v[32];
+                tmem_ld32(tmem_S + lane_off + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const int k0 = c * 32 + 2 * i;
+                  const float x0 = (k0 < valid) ? fmaf(__uint_as_float(v[2 * i]), sl, -m_sl) : -INFINITY;
+                  const float x1 = (k0 + 1 < valid) ? fmaf(__uint_as_float(v[2 * i + 1]), sl, -m_sl) : -INFINITY;
+                  pk[c * 16 + i] = ex2_h2(x0, x1);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) pk[c * 16 + i] = 0u;
+              }
             }
           }
           tc_fence_before();
@@ -1471,6 +1487,10 @@ attention_pair_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __g
           }
         }
         m_run = m_new;
+        if (j == 0 && it > 0) {  // the output tile of the previous item sits in P slab 0 until its TMA store has read it
+          if (warp == 0 && store_issuer) bulk_wait_group_read<0>();
+          named_bar_sync(1, 128);
+        }
 #pragma unroll
         for (int cc = 0; cc < 16; ++cc) {
           uint8_t* slab = sP + (cc >> 3) * kSlab + r * 128;
@@ -1490,50 +1510,64 @@ attention_pair_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __g
         if (lane0) mbar_arrive_cluster(p_full_lead);
       }
       // ---- output of this item: O / l -> global, then hand the accumulator back ----
+      if (r == 0) stamp(g - 1, 11);
       mbar_wait(pv_done, (g - 1) & 1);
       tc_fence_after();
-      float inv_l;
-      {
-        uint32_t o[16];
-        tmem_ld16(tO + (p.d & ~15), o);
-        tmem_ld_wait();
-        float l = 1.f;
+      if (r == 0) stamp(g - 1, 12);
+      // The normalised tile goes to global memory as ONE TMA store out of P slab 0 (free until the next item's first
+      // P): per-row 16-byte STGs (128 rows x 640-byte stride) clogged the LSU queue in front of the next mbarrier
+      // polls and cost 1 700 clk per item in the clock64 trace. Rows >= s_q and columns >= d are clipped by the map.
+      uint32_t o[64];
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (i == (p.d & 15)) l = __uint_as_float(o[i]);
-        inv_l = 1.f / l;
+      for (int c = 0; c < 64; c += 16) {
+        uint32_t t16[16];
+        tmem_ld16(tO + c, t16);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[c + i] = t16[i];
       }
-      const int row = q0 + r;
-      __half* orow = p.o + (static_cast<long long>(nb) * p.s_q + row) * p.o_ld + static_cast<long long>(head) * p.d;
-      const bool vec_ok = ((reinterpret_cast<uintptr_t>(orow) & 15) == 0);
-      for (int c = 0; c < p.d; c += 16) {
-        uint32_t o[16];
-        tmem_ld16(tO + c, o);
-        tmem_ld_wait();
-        if (row < p.s_q) {
+      const uint32_t lbits = tmem_ld1(tO + p.d);  // denominator = accumulator column d
+      tmem_ld_wait();
+      const float inv_l = __fdividef(1.f, __uint_as_float(lbits));
+      {
+        uint8_t* srow = sP + r * 128;
 #pragma unroll
-          for (int h2 = 0; h2 < 2; ++h2) {
-            const int col = c + h2 * 8;
-            if (col + 8 <= p.d && vec_ok) {
-              uint32_t q4[4];
+        for (int c8 = 0; c8 < 7; ++c8) {
+          if (c8 * 8 < p.d) {
+            uint32_t q4[4];
 #pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                __half2 h = __floats2half2_rn(__uint_as_float(o[h2 * 8 + 2 * t]) * inv_l,
-                                              __uint_as_float(o[h2 * 8 + 2 * t + 1]) * inv_l);
-                q4[t] = *reinterpret_cast<uint32_t*>(&h);
-              }
-              *reinterpret_cast<uint4*>(orow + col) = make_uint4(q4[0], q4[1], q4[2], q4[3]);
-            } else {
-              for (int i = 0; i < 8; ++i)
-                if (col + i < p.d) orow[col + i] = __float2half_rn(__uint_as_float(o[h2 * 8 + i]) * inv_l);
+            for (int t = 0; t < 4; ++t) {
+              __half2 h = __floats2half2_rn(__uint_as_float(o[c8 * 8 + 2 * t]) * inv_l,
+                                            __uint_as_float(o[c8 * 8 + 2 * t + 1]) * inv_l);
+              q4[t] = *reinterpret_cast<uint32_t*>(&h);
             }
+            *reinterpret_cast<uint4*>(srow + ((c8 ^ (r & 7)) << 4)) = make_uint4(q4[0], q4[1], q4[2], q4[3]);
           }
         }
       }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      named_bar_sync(1, 128);
+      if (warp == 0 && store_issuer) {
+        tma_store_4d(&tmO, sP, 0, head, q0, nb);
+        bulk_commit_group();
+      }
       tc_fence_before();
       __syncwarp();
+      if (r == 0) stamp(g - 1, 13);
       if (lane0) mbar_arrive_cluster(mapa_shared(smem_u32(&o_empty[it & 1]), 0));
+      qp += d_qp;
+      head += d_head;
+      nb += d_nb;
+      if (qp >= pp.n_qpairs) {
+        qp -= pp.n_qpairs;
+        ++head;
+      }
+      if (head >= pp.heads) {
+        head -= pp.heads;
+        ++nb;
+      }
     }
+    if (warp == 0 && store_issuer) bulk_wait_group<0>();  // output stores complete before the CTA may exit
   }
 
   tc_fence_before();
@@ -1547,7 +1581,8 @@ attention_pair_persist_kernel(const __grid_constant__ CUtensorMap tmQ, const __g
 
 template <int NS, int POLY>
 static int launch_attn_pair_persist(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-                                    const AttnParams& ap, const AttnPersist& pp, cudaStream_t stream) {
+                                    const CUtensorMap& to, const AttnParams& ap, const AttnPersist& pp,
+                                    cudaStream_t stream) {
   constexpr int smem = attnpp_smem_bytes<NS>();
   constexpr int kPerSm = smem <= 113 * 1024 ? 2 : 1;
   static_assert(smem <= 227 * 1024, "persistent pair attention exceeds shared memory");
@@ -1582,7 +1617,7 @@ static int launch_attn_pair_persist(const CUtensorMap& tq, const CUtensorMap& tk
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  IVV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, ap, pp));
+  IVV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tq, tk, tv, to, ap, pp));
   return 0;
 }
 
@@ -1666,7 +1701,13 @@ extern "C" int ivv_attention(const void* q, int64_t q_ld, const void* k, const v
   // IVV_ATTN_PAIR=0 falls back to the one-tile kernel, IVV_ATTN_POLY=0 keeps every exponential on the MUFU
   {
     const char* f = getenv("IVV_ATTN_PAIR");
-    const bool pair = dc == 1 && s_q > kQ && s_kv > kKV && (f ? atoi(f) != 0 : true);
+    // single-block problems (cross-attention, 77 keys) also go through the persistent pair kernel: its Q / O double
+    // buffering overlaps one item's loads and output with the next (82 -> 55 us at S_q = 1536); IVV_ATTN_PAIR_SHORT=0
+    // sends them back to the one-tile kernel
+    const char* f1 = getenv("IVV_ATTN_PAIR_SHORT");
+    const bool short_ok = s_kv > kKV || !(f1 && atoi(f1) == 0);
+    const bool pair = dc == 1 && s_q > kQ && short_ok && (reinterpret_cast<uintptr_t>(o) & 15) == 0 &&
+                      (f ? atoi(f) != 0 : true);
     if (pair) {
       CUtensorMap tk64;
       const uint32_t box64[4] = {64, 1, 64, 1};
@@ -1684,10 +1725,16 @@ extern "C" int ivv_attention(const void* q, int64_t q_ld, const void* k, const v
         pp.n_qpairs = (int)((tiles + 1) / 2);
         pp.heads = heads;
         pp.n_items = pp.n_qpairs * heads * (int)n_batch;
+        CUtensorMap to;
+        {
+          const uint64_t odims[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)s_q, (uint64_t)n_batch};
+          const uint64_t ostr[4] = {2, (uint64_t)d * 2, (uint64_t)o_ld * 2, (uint64_t)o_ld * 2 * s_q};
+          if (int rc = make_tmap_f16(&to, o, 4, odims, ostr, box, 128)) return rc;
+        }
         const char* ns = getenv("IVV_ATTN_NS");
-        if (ns && atoi(ns) == 6) return launch_attn_pair_persist<6, 0>(tq, tk64, tv, ap, pp, stream);
-        return poly ? launch_attn_pair_persist<2, 1>(tq, tk64, tv, ap, pp, stream)
-                    : launch_attn_pair_persist<2, 0>(tq, tk64, tv, ap, pp, stream);
+        if (ns && atoi(ns) == 6) return launch_attn_pair_persist<6, 0>(tq, tk64, tv, to, ap, pp, stream);
+        return poly ? launch_attn_pair_persist<2, 1>(tq, tk64, tv, to, ap, pp, stream)
+                    : launch_attn_pair_persist<2, 0>(tq, tk64, tv, to, ap, pp, stream);
       }
       if (const char* dbg = getenv("IVV_ATTN_DBG")) {  // timing experiments (tools/attn_bench.py); garbage results
         switch (atoi(dbg)) {

@@ -566,7 +566,7 @@ class _Engine:
         # cross-attention: K/V once per clip (the reference repeats ctx per frame, attention.py:96)
         nrm = ops.layernorm(hs, *p["ln2"][:2], eps=p["ln2"][2])
         q = ops.linear(nrm, p["attn2"]["q"])
-        kv = ops.linear(st["ctx"], p["attn2"]["kv"])
+        kv = st["ctx_kv"][name]  # projected once per context, not once per denoising step (_context_kv)
         ao = ops.attention(q, _Col(kv, 0), _Col(kv, c), n_batch=n, s_q=s, s_kv=st["ctx_len"], heads=heads, d=d,
                            q_ld=c, kv_ld=2 * c, kv_div=f)
         hs = ops.linear(ao, p["attn2"]["out"][0], bias=p["attn2"]["out"][1], residual=hs)
@@ -596,11 +596,25 @@ class _Engine:
             hs = ops.linear(g, blk["ff"]["out"][0], bias=blk["ff"]["out"][1], residual=hs)
         return ops.linear(hs, p["pout"][0], bias=p["pout"][1], residual=x)
 
+    # ---- cross-attention K/V of the text context ---------------------------------------------------------------
+    def _context_kv(self, ctx, out=None):
+        """to_k / to_v of every spatial transformer block applied to the context (attention.py:241-256 computes them
+        inside each forward). They depend on the context only, which the sampler keeps fixed over all DDIM steps
+        (inference.py:183-194), so they are projected once per context into `out` (static
+        buffers of a CUDA graph) or fresh tensors. Returns {block name: [b*77, 2C] fp16}."""
+        c16 = ctx.reshape(-1, ctx.shape[-1]).to(F16).contiguous()
+        kvs = {}
+        for step in self.plan:
+            if step[0] == "spatial":
+                name = step[1]
+                kvs[name] = ops.linear(c16, self.w[name]["attn2"]["kv"], out=None if out is None else out[name])
+        return kvs
+
     # ---- one forward ---------------------------------------------------------------------------------------
-    def _forward_frames(self, sample, t, ctx, pe_start):
+    def _forward_frames(self, sample, t, ctx, pe_start, ctx_kv=None):
         b, cin, f, h, w = sample.shape
         st = dict(b=b, f=f, n=b * f, h=h, w=w, pe_start=pe_start)
-        st["ctx"] = ctx.reshape(-1, ctx.shape[-1]).to(F16).contiguous()
+        st["ctx_kv"] = self._context_kv(ctx) if ctx_kv is None else ctx_kv
         st["ctx_len"] = ctx.shape[1]
         W = self.w
         # time embedding: sinusoid -> linear_1 -> SiLU -> linear_2 -> SiLU -> all time_emb_proj at once
@@ -665,30 +679,38 @@ class _Engine:
 
 class _Graph:
     """CUDA-graph capture of one forward: static input buffers, one cudaGraphLaunch per UNet call instead of ~1200
-    kernel launches issued from Python."""
+    kernel launches issued from Python. The cross-attention K/V projections of the context live in static buffers that
+    are refreshed (16 small GEMMs, eagerly) only when the caller passes a different or modified context tensor - the
+    sampler passes the same one for all DDIM steps of a clip."""
 
     def __init__(self, eng, sample, t, ctx, pe_start):
+        self.eng = eng
         self.s_in = sample.clone()
         self.t_in = t.clone()
         self.c_in = ctx.clone()
+        self.ctx_ref, self.ctx_ver = None, -1  # the context object the static K/V were computed from
         stream = torch.cuda.Stream(device=sample.device)
         stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(stream):
-            eng._forward_frames(self.s_in, self.t_in, self.c_in, pe_start)  # warm-up: lazy kernel attribute setup
+            self.ctx_kv = eng._context_kv(self.c_in)
+            eng._forward_frames(self.s_in, self.t_in, self.c_in, pe_start, self.ctx_kv)  # warm-up: lazy kernel setup
         torch.cuda.current_stream().wait_stream(stream)
         torch.cuda.synchronize()
         from . import lib as _lib
         n0 = _lib.LAUNCH_COUNT
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.out = eng._forward_frames(self.s_in, self.t_in, self.c_in, pe_start)
+            self.out = eng._forward_frames(self.s_in, self.t_in, self.c_in, pe_start, self.ctx_kv)
         self.n_launches = _lib.LAUNCH_COUNT - n0  # kernels inside the graph: counted again on every replay
         self._lib = _lib
 
     def replay(self, sample, t, ctx):
         self.s_in.copy_(sample)
         self.t_in.copy_(t)
-        self.c_in.copy_(ctx)
+        if ctx is not self.ctx_ref or ctx._version != self.ctx_ver:
+            self.c_in.copy_(ctx)
+            self.eng._context_kv(self.c_in, out=self.ctx_kv)
+            self.ctx_ref, self.ctx_ver = ctx, ctx._version  # holding the reference keeps its storage from being reused
         self.graph.replay()
         self._lib.LAUNCH_COUNT += self.n_launches
         return self.out.clone()

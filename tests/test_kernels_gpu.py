@@ -392,6 +392,7 @@ print("variant ok")
                                  {"IVV_ATTN_PAIR": "0", "IVV_ATTN_TWO_TILE": "1"}, {"IVV_ATTN_PAIR": "0"},
                                  {"IVV_ATTN_PAIR": "0", "IVV_ATTN_QK_FIRST": "0"}, {"IVV_ATTN_MODE": "0"},
                                  {"IVV_ATTN_MODE": "1"}, {"IVV_ATTN_MODE": "2"}, {"IVV_ATTN_POLY": "1"},
+                                 {"IVV_ATTN_PAIR_SHORT": "0"},
                                  {"IVV_ATTN_MODE": "0", "IVV_ATTN_POLY": "1"},
                                  {"IVV_FORCE_BN": "128"}, {"IVV_FORCE_BN": "256"}])
 def test_kernel_variants(env):

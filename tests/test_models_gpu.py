@@ -50,6 +50,28 @@ def test_unet_vs_reference_golden(tag, case, graph):
         _check(f"unet {tag}/{case} graph={graph} rep={rep}", y, g["out"])
 
 
+def test_unet_context_kv_cache():
+    """The captured graph keeps the cross-attention K/V of the context in static buffers and refreshes them only when
+    the context changes: same object -> reused; modified in place or a new tensor -> recomputed. Every call must equal
+    the eager (no graph, K/V projected inside the forward) result for the context it was given."""
+    m, cfg, _ = _unet("micro")
+    x = seeded((1, 8, 4, 16, 16), 1).cuda()
+    t = torch.tensor([500], device="cuda")
+    ctx_a = seeded((1, 77, cfg["cross_attention_dim"]), 2).cuda()
+    ctx_b = seeded((1, 77, cfg["cross_attention_dim"]), 3).cuda()
+    m.use_cuda_graph = False
+    ref_a = m(x, t, encoder_hidden_states=ctx_a).sample
+    ref_b = m(x, t, encoder_hidden_states=ctx_b).sample
+    assert (ref_a - ref_b).abs().max() > 1e-3 * ref_a.abs().max()  # the context matters
+    m.use_cuda_graph = True
+    for _ in range(3):
+        assert torch.equal(m(x, t, encoder_hidden_states=ctx_a).sample, ref_a)
+    assert torch.equal(m(x, t, encoder_hidden_states=ctx_b).sample, ref_b)      # different tensor
+    ctx_a.copy_(ctx_b)                                                          # same object, modified in place
+    assert torch.equal(m(x, t, encoder_hidden_states=ctx_a).sample, ref_b)
+    assert torch.equal(m(x, t, encoder_hidden_states=ctx_a).sample, ref_b)
+
+
 def test_unet_api_contract():
     m, cfg, _ = _unet("micro")
     x = seeded((1, 8, 4, 16, 16), 1).cuda()

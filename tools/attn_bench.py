@@ -12,13 +12,12 @@ sys.path.insert(0, ROOT)
 SHAPES = [(48, 1536, 1536, 8, 40, 1), (48, 1536, 77, 8, 40, 16), (48, 384, 384, 8, 80, 1), (48, 96, 96, 8, 160, 1)]
 VARIANTS = [
     {"IVV_ATTN_PAIR": "0"},
-    {"IVV_ATTN_PAIR": "1", "IVV_ATTN_MODE": "0"},
-    {"IVV_ATTN_PAIR": "1", "IVV_ATTN_MODE": "1"},
     {"IVV_ATTN_PAIR": "1", "IVV_ATTN_MODE": "3"},
+    {"IVV_ATTN_PAIR": "1", "IVV_ATTN_MODE": "3", "IVV_ATTN_PAIR_SHORT": "1"},
     {"IVV_ATTN_PAIR": "1", "IVV_ATTN_MODE": "3", "IVV_ATTN_POLY": "1"},
 ]
 if os.environ.get("ATTN_BENCH_ONE"):
-    SHAPES = SHAPES[:1]
+    SHAPES = SHAPES[:2]
 
 
 def child():

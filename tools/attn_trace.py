@@ -29,8 +29,8 @@ L.ivv_debug_attn_trace(None)
 t = buf.cpu()
 t0 = int(t[t > 0].min())
 names = {0: "S seen", 1: "S freed", 9: "wait PV", 2: "PV seen", 10: "P stored", 3: "P signal", 4: "mma:Sfree", 5: "mma:QK",
-         6: "mma:P seen", 7: "mma:PV iss", 8: "tma:slot"}
-order = [8, 5, 0, 1, 4, 9, 2, 10, 3, 6, 7]
+         6: "mma:P seen", 7: "mma:PV iss", 8: "tma:slot", 11: "out:start", 12: "out:PV ok", 13: "out:done"}
+order = [8, 5, 0, 1, 4, 9, 2, 10, 3, 6, 7, 11, 12, 13]
 print("block " + " ".join(f"{names[k]:>10s}" for k in order))
-for g in range(28):
+for g in range(10, 27):
     print(f"{g:5d} " + " ".join(f"{(int(t[g, k]) - t0) if t[g, k] > 0 else -1:10d}" for k in order))

@@ -43,6 +43,6 @@ if __name__ == "__main__":
     if len(sys.argv) > 1:
         child()
     else:
-        for pair in ["0"]:
+        for pair in ["1"]:
             for skip in ["0", "1", "2", "3"]:
                 subprocess.run([sys.executable, __file__, "child"], env=dict(os.environ, IVV_PAIR=pair, IVV_DEBUG_SKIP=skip))
