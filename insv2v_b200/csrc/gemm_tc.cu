@@ -31,6 +31,7 @@ struct GemmKParams {
   int ws_stages;                  // >0: weight-stationary mode (persistent kernel): the CTA's weight tile (all of K) is
                                   // loaded once and stays in shared memory; only A tiles stream through ws_stages slots
   int dbg_skip;                   // tuning only (IVV_DEBUG_SKIP): 1 = no MMA issue, 2 = no TMA loads (results are garbage)
+  int halo_bytes;                 // HALO kernels: bytes of one (bw x (bh + 2)) activation box = (bh + 2) * bw * 128
   void* d;
   long long d_ld;
   const __half* bias;
@@ -310,13 +311,18 @@ template <int BN>
 constexpr uint32_t acc_stride_for() {
   return BN <= 32 ? 32u : BN <= 64 ? 64u : BN <= 128 ? 128u : 256u;
 }
-template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, bool TWO = false>
+// HALO (3x3 convolutions, pair mode): one stage holds a (bw x (bh + 2)) activation box -- at most kHaloRows pixel rows of
+// 64 channels -- and the three weight tiles of the filter column it serves (dy = -1, 0, +1).
+constexpr int kHaloRows = 160;
+constexpr int kHaloBytes = kHaloRows * 128;  // 20 KB, a multiple of the 1024-B swizzle atom
+template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, bool TWO = false, bool HALO = false>
 constexpr int persist_smem_bytes() {
   // TILEWIDE: the whole fp16 output tile is staged; otherwise one CW-wide slab per epilogue group
-  return STAGES * (kABytes + (TWO ? BN / 2 : BN) * 128) + (TILEWIDE ? kBlockM * (GEGLU ? BN / 2 : BN) * 2 : 2 * kBlockM * CW * 2) + 256;
+  return STAGES * (HALO ? kHaloBytes + 3 * (BN / 2) * 128 : kABytes + (TWO ? BN / 2 : BN) * 128) +
+         (TILEWIDE ? kBlockM * (GEGLU ? BN / 2 : BN) * 2 : 2 * kBlockM * CW * 2) + 256;
 }
 
-template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, int CS, bool TWO>
+template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, int CS, bool TWO, bool HALO = false>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                           const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
@@ -328,9 +334,17 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   // TWO: the pair runs ONE tcgen05.mma.cta_group::2 (M = 256): each CTA stages its own 128 A rows and only HALF of the
   // weight tile, which is what lifts the ~60 B/clk per-SM operand-ingest limit of the single-CTA kernel.
+  // HALO (3x3, stride 1, box inside one frame, bw % 8 == 0): the three taps of one filter COLUMN read the same pixels
+  // shifted by whole box rows, so ONE (bw x (bh + 2)) box per (dx, 64-channel block) serves all three: the MMA of tap
+  // dy starts (dy + 1) * bw rows into the box (a multiple of the 8-row swizzle atom, so the descriptor stays canonical).
+  // Activation bytes per tile drop from 9 x 16 KB to 3 x <= 20 KB per channel block: these GEMMs are bound by the
+  // ~6300 B/clk the L2 can deliver chip-wide, not by the tensor pipe.
   static_assert(!TWO || CS == 2, "pair MMA needs a 2-CTA cluster");
+  static_assert(!HALO || (TWO && !GEGLU), "halo mode is built on the pair kernel");
   constexpr int kBRows = TWO ? BN / 2 : BN;
-  constexpr int kStageBytes = kABytes + kBRows * 128;
+  constexpr int kBTileBytes = kBRows * 128;
+  constexpr int kAOff = HALO ? kHaloBytes : kABytes;  // offset of the weight tile(s) inside a stage
+  constexpr int kStageBytes = kAOff + (HALO ? 3 : 1) * kBTileBytes;
   constexpr uint16_t kMask = (1u << CS) - 1;
   const int crank = CS > 1 ? (int)cluster_ctarank() : 0;
   const int tile_first = CS > 1 ? (int)cluster_id_x() : (int)blockIdx.x;
@@ -350,7 +364,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int its_per_tile = p.taps * p.kblocks;
+  const int its_per_tile = (HALO ? 3 : p.taps) * p.kblocks;  // HALO: one iteration = (filter column, channel block)
   // weight-stationary layout of the same stage region: [its_per_tile x (BN x 128 B) resident B][ws_stages x 16 KB A ring]
   const bool ws = !TWO && CS == 1 && p.ws_stages > 0;
   uint8_t* b_res = smem;
@@ -414,6 +428,22 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
+          if constexpr (HALO) {
+            const int dxi = it / p.kblocks;  // filter column 0..2 (dx = dxi - 1)
+            const int kc = (it - dxi * p.kblocks) * kBlockK;
+            const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * (p.halo_bytes + 3 * kBTileBytes));
+            tma_load_4d_2sm(sa, &tmA, lead_bar, kc, w0 + dxi - 1, h0 - 1, n0);
+#pragma unroll
+            for (int dyi = 0; dyi < 3; ++dyi)
+              tma_load_3d_2sm(sa + kAOff + dyi * kBTileBytes, &tmB, lead_bar, kc, ntile * BN + crank * kBRows,
+                              dyi * 3 + dxi);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           if constexpr (TWO) {
             // bytes of BOTH CTAs are counted on the leader's barrier. The peer needs no arrive of its own: it can only
             // refill a stage after the leader's MMA released it, i.e. after the leader's barrier finished that phase.
@@ -475,6 +505,22 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = ws ? smem_u32(a_ring + stage * kABytes) : smem_u32(smem + stage * kStageBytes);
+          if constexpr (HALO) {
+#pragma unroll
+            for (int dyi = 0; dyi < 3; ++dyi) {
+              const uint64_t adesc = umma_desc_kmajor_sw128(sa + dyi * p.bw * 128);
+              const uint64_t bdesc = umma_desc_kmajor_sw128(sa + kAOff + dyi * kBTileBytes);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_f16_ss_2sm(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | dyi | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_2sm(&empty_bar[stage], kMask);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           const uint64_t adesc = umma_desc_kmajor_sw128(sa);
           const uint64_t bdesc = umma_desc_kmajor_sw128(ws ? smem_u32(b_res + it * (BN * 128)) : sa + kABytes);
 #pragma unroll
@@ -716,14 +762,20 @@ static int pow2_ceil(long long x) {
 }
 
 // choose the (bw, bh, bn) pixel box with bw*bh*bn = 128 that minimises the number of M tiles
-static void choose_box(long long W, long long H, long long NI, int* bw, int* bh, int* bn) {
+// halo mode needs the box inside one frame, whole swizzle atoms per box row and (bh + 2) * bw <= kHaloRows
+static bool halo_box_ok(int bw, int bh, int bn) { return bn == 1 && (bw % 8) == 0 && (bh + 2) * bw <= kHaloRows; }
+
+static void choose_box(long long W, long long H, long long NI, bool want_halo, int* bw, int* bh, int* bn) {
   long long best = -1;
   for (int cw = 1; cw <= 128; cw *= 2) {
     for (int ch = 1; cw * ch <= 128; ch *= 2) {
       const int cn = 128 / (cw * ch);
       const long long tiles = ((W + cw - 1) / cw) * ((H + ch - 1) / ch) * ((NI + cn - 1) / cn);
-      // prefer fewer tiles; tie -> wider rows (longer contiguous runs in memory)
-      if (best < 0 || tiles < best || (tiles == best && cw > *bw)) {
+      // prefer fewer tiles; tie -> (3x3 convolutions) a box the halo kernel takes, then wider rows (longer contiguous
+      // runs in memory)
+      const bool halo_new = want_halo && halo_box_ok(cw, ch, cn);
+      const bool halo_old = best >= 0 && want_halo && halo_box_ok(*bw, *bh, *bn);
+      if (best < 0 || tiles < best || (tiles == best && (halo_new > halo_old || (halo_new == halo_old && cw > *bw)))) {
         best = tiles;
         *bw = cw;
         *bh = ch;
@@ -745,13 +797,13 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, int CS, bool TWO = false>
+template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, int CS, bool TWO = false, bool HALO = false>
 static int launch_persistent_cs(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                                 const CUtensorMap& tmR, const GemmKParams& kp, int m_tiles, int n_tiles,
                                 cudaStream_t stream) {
-  constexpr int smem = persist_smem_bytes<BN, STAGES, CW, GEGLU, TILEWIDE, TWO>();
+  constexpr int smem = persist_smem_bytes<BN, STAGES, CW, GEGLU, TILEWIDE, TWO, HALO>();
   static_assert(smem <= 227 * 1024, "persistent GEMM configuration exceeds shared memory");
-  auto kern = gemm_tc_persistent_kernel<BN, STAGES, CW, GEGLU, TILEWIDE, CS, TWO>;
+  auto kern = gemm_tc_persistent_kernel<BN, STAGES, CW, GEGLU, TILEWIDE, CS, TWO, HALO>;
   static bool configured = false;
   if (!configured) {
     IVV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -835,7 +887,11 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
   IVV_REQUIRE(!(a->geglu && (a->rowbias || a->residual)), "ivv_gemm: GEGLU epilogue takes bias only");
 
   GemmKParams kp{};
-  choose_box(a->w, a->h, a->n_img, &kp.bw, &kp.bh, &kp.bn);
+  // 3x3 convolutions on fp16 outputs may take the halo kernel (one activation box per filter column); IVV_HALO=0 disables
+  const bool want_halo = a->taps == 9 && tap_h == 3 && tap_w == 3 && !a->geglu && !a->out_f32 && a->splits <= 1 &&
+                         !(getenv("IVV_HALO") && atoi(getenv("IVV_HALO")) == 0);
+  choose_box(a->w, a->h, a->n_img, want_halo, &kp.bw, &kp.bh, &kp.bn);
+  kp.halo_bytes = (kp.bh + 2) * kp.bw * 128;
   kp.tiles_w = (int)((a->w + kp.bw - 1) / kp.bw);
   kp.tiles_h = (int)((a->h + kp.bh - 1) / kp.bh);
   kp.tiles_g = (int)((a->n_img + kp.bn - 1) / kp.bn);
@@ -873,6 +929,13 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
   const long long m_tiles_ll = (long long)kp.tiles_w * kp.tiles_h * kp.tiles_g;
   IVV_REQUIRE(m_tiles_ll <= 65535, "ivv_gemm: too many M tiles (%lld)", m_tiles_ll);
   const int m_tiles = (int)m_tiles_ll;
+  const bool res_ok = a->residual == nullptr ||
+                      ((a->res_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0);
+  const bool persistent_ok = !a->out_f32 && (a->d_ld % 8) == 0 && ((reinterpret_cast<uintptr_t>(a->d) & 15) == 0) && res_ok;
+  // the halo kernel is a pair-mode persistent kernel with 128/160/256-wide tiles
+  const bool halo = want_halo && halo_box_ok(kp.bw, kp.bh, kp.bn) && persistent_ok && m_tiles >= 2 && a->n_out >= 96 &&
+                    !(getenv("IVV_PAIR") && atoi(getenv("IVV_PAIR")) == 0) && getenv("IVV_CLUSTER") == nullptr &&
+                    getenv("IVV_FORCE_BN") == nullptr;
 
   // ---- tile-N choice: least padding first, then enough CTAs to fill 148 SMs ----
   int bn_sel;
@@ -884,13 +947,15 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
     const int cands[5] = {256, 160, 128, 64, 32};
     double best = 1e30;
     bn_sel = 128;
-    for (int i = 0; i < 5; ++i) {
+    // halo mode: a pair fetches 2 * (bh + 2) * bw activation rows per three taps instead of 2 * 128 per tap
+    const double a_rows = halo ? 2.0 * (kp.bh + 2) * kp.bw / 3.0 : 256.0;
+    for (int i = 0; i < (halo ? 3 : 5); ++i) {
       const long long nt = (a->n_out + cands[i] - 1) / cands[i];
       const double waste = (double)nt * cands[i] / (double)a->n_out;
       const long long tiles = nt * m_tiles * (a->splits > 1 ? a->splits : 1);
       const long long waves = (tiles + sm_count() - 1) / sm_count();
       const double eff = (double)tiles / (double)(waves * sm_count());
-      const double cost = waste * (1.0 / cands[i] + (m_tiles >= 2 ? 1.0 / 256.0 : 1.0 / 128.0)) / eff;
+      const double cost = waste * (a_rows / 256.0 / cands[i] + (m_tiles >= 2 ? 1.0 / 256.0 : 1.0 / 128.0)) / eff;
       if (cost < best * 0.999) {
         best = cost;
         bn_sel = cands[i];
@@ -911,7 +976,7 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
     const uint64_t dims[4] = {(uint64_t)a->c, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n_img};
     const uint64_t strides[4] = {2, (uint64_t)a->a_ld * 2, (uint64_t)a->a_ld * 2 * a->w,
                                  (uint64_t)a->a_ld * 2 * a->w * a->h};
-    const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)kp.bw, (uint32_t)kp.bh, (uint32_t)kp.bn};
+    const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)kp.bw, (uint32_t)(halo ? kp.bh + 2 : kp.bh), (uint32_t)kp.bn};
     if (int rc = make_tmap_f16(&tmA, a->a, 4, dims, strides, box, 128)) return rc;
   }
   {
@@ -923,12 +988,9 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
     if (int rc = make_tmap_f16(&tmB2, a->wgt, 3, dims, strides, box2, 128)) return rc;
   }
 
-  const bool res_ok = a->residual == nullptr ||
-                      ((a->res_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(a->residual) & 15) == 0);
-  const bool persistent = !a->out_f32 && (a->d_ld % 8) == 0 && ((reinterpret_cast<uintptr_t>(a->d) & 15) == 0) &&
-                          res_ok && (long long)m_tiles * n_tiles < (1LL << 30);
+  const bool persistent = persistent_ok && (long long)m_tiles * n_tiles < (1LL << 30);
   if (persistent) {
-    const int cw = a->geglu ? 32 : (bn_sel == 256 || bn_sel == 128) ? 64 : 32;
+    const int cw = a->geglu ? 32 : halo ? (bn_sel == 128 ? 64 : 32) : (bn_sel == 256 || bn_sel == 128) ? 64 : 32;
     CUtensorMap tmD, tmR;
     const uint32_t box[4] = {(uint32_t)cw, (uint32_t)kp.bw, (uint32_t)kp.bh, (uint32_t)kp.bn};
     {
@@ -964,6 +1026,19 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
     // CTA pairs (tcgen05.mma.cta_group::2, M = 256): default whenever there are at least two M tiles
     bool pair = m_tiles >= 2 && kp.ws_stages == 0;
     if (const char* f = getenv("IVV_PAIR")) pair = pair && atoi(f) != 0;
+    if (halo) {
+      // stage = 20 KB activation box + 3 half weight tiles; ring staging where the main loop (>= 15 iterations of 12
+      // MMAs) hides the epilogue anyway
+      kp.ws_stages = 0;
+      switch (bn_sel) {
+        case 256:
+          return launch_persistent_cs<256, 3, 32, false, false, 2, true, true>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
+        case 160:
+          return launch_persistent_cs<160, 4, 32, false, false, 2, true, true>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
+        default:
+          return launch_persistent_cs<128, 4, 64, false, true, 2, true, true>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
+      }
+    }
     if (pair && cs == 1) {
 #define IVV_PAIR_LAUNCH(BN_, ST_, CW_, GG_, TW_) \
   return launch_persistent_cs<BN_, ST_, CW_, GG_, TW_, 2, true>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream)

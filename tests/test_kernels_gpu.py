@@ -98,7 +98,12 @@ def _nchw(fr, n, h, w):
 
 @pytest.mark.parametrize("n,ci,co,h,w", [(2, 64, 64, 16, 16), (6, 320, 320, 32, 48), (4, 8, 320, 32, 48),
                                          (5, 640, 1280, 8, 12), (48, 1280, 1280, 4, 6), (3, 128, 8, 12, 20),
-                                         (2, 192, 320, 5, 7)])
+                                         (2, 192, 320, 5, 7),
+                                         # halo kernel (one activation box per filter column): 8x16 box with 160-wide
+                                         # tiles, 256- and 128-wide tiles, ragged tiles in both directions, an odd
+                                         # number of M tiles (ghost tile of the CTA pair), channel tail (ci % 64 != 0)
+                                         (3, 640, 640, 16, 24), (2, 128, 512, 32, 48), (2, 64, 128, 24, 40),
+                                         (1, 96, 320, 20, 44), (3, 200, 256, 8, 16)])
 def test_conv3x3(n, ci, co, h, w):
     ops = _ops()
     x = h16(n, ci, h, w, seed=1)
@@ -109,9 +114,10 @@ def test_conv3x3(n, ci, co, h, w):
     report(f"conv3x3 n{n} {ci}->{co} {h}x{w}", _nchw(out, n, h, w), ref)
 
 
-def test_conv3x3_fused_temb_residual():
+@pytest.mark.parametrize("h,w", [(8, 12), (16, 24), (32, 48)])  # the two larger ones take the halo kernel
+def test_conv3x3_fused_temb_residual(h, w):
     ops = _ops()
-    b_, f, ci, co, h, w = 2, 4, 128, 192, 8, 12
+    b_, f, ci, co = 2, 4, 128, 192
     n = b_ * f
     x = h16(n, ci, h, w, seed=1)
     wt = h16(co, ci, 3, 3, scale=(9 * ci) ** -0.5, seed=2)
@@ -394,7 +400,7 @@ print("variant ok")
                                  {"IVV_ATTN_MODE": "1"}, {"IVV_ATTN_MODE": "2"}, {"IVV_ATTN_POLY": "1"},
                                  {"IVV_ATTN_PAIR_SHORT": "0"},
                                  {"IVV_ATTN_MODE": "0", "IVV_ATTN_POLY": "1"},
-                                 {"IVV_FORCE_BN": "128"}, {"IVV_FORCE_BN": "256"}])
+                                 {"IVV_FORCE_BN": "128"}, {"IVV_FORCE_BN": "256"}, {"IVV_HALO": "0"}])
 def test_kernel_variants(env):
     """The opt-in / fallback code paths (single-CTA GEMM, multicast clusters, two-tile attention, other tile widths)
     stay correct: same checks in a subprocess with the tuning environment variables set."""
