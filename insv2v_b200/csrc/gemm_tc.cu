@@ -315,14 +315,14 @@ constexpr uint32_t acc_stride_for() {
 // 64 channels -- and the three weight tiles of the filter column it serves (dy = -1, 0, +1).
 constexpr int kHaloRows = 160;
 constexpr int kHaloBytes = kHaloRows * 128;  // 20 KB, a multiple of the 1024-B swizzle atom
-template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, bool TWO = false, bool HALO = false>
+template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, bool TWO = false, bool HALO = false, bool DS = false>
 constexpr int persist_smem_bytes() {
-  // TILEWIDE: the whole fp16 output tile is staged; otherwise one CW-wide slab per epilogue group
+  // TILEWIDE: the whole fp16 output tile is staged (DS: two such slabs); otherwise one CW-wide slab per epilogue group
   return STAGES * (HALO ? kHaloBytes + 3 * (BN / 2) * 128 : kABytes + (TWO ? BN / 2 : BN) * 128) +
-         (TILEWIDE ? kBlockM * (GEGLU ? BN / 2 : BN) * 2 : 2 * kBlockM * CW * 2) + 256;
+         (TILEWIDE ? (DS ? 2 : 1) * kBlockM * (GEGLU ? BN / 2 : BN) * 2 : 2 * kBlockM * CW * 2) + 256;
 }
 
-template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, int CS, bool TWO, bool HALO = false>
+template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, int CS, bool TWO, bool HALO = false, bool DS = false>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                           const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
@@ -341,6 +341,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   // ~6300 B/clk the L2 can deliver chip-wide, not by the tensor pipe.
   static_assert(!TWO || CS == 2, "pair MMA needs a 2-CTA cluster");
   static_assert(!HALO || (TWO && !GEGLU), "halo mode is built on the pair kernel");
+  // DS (tile-wide staging, residual GEMMs with short main loops): TWO staging slabs used alternately. With one slab the
+  // residual tile of tile i+1 can only be requested after the store of tile i has drained it, so every tile pays a full
+  // HBM round trip in its epilogue -- with K <= 640 that chain (not the main loop) set the pace. With two, the residual
+  // of tile i+1 is requested when the epilogue of tile i STARTS and has a whole tile period to land.
+  static_assert(!DS || (TILEWIDE && !GEGLU), "double staging belongs to the tile-wide residual epilogue");
   constexpr int kBRows = TWO ? BN / 2 : BN;
   constexpr int kBTileBytes = kBRows * 128;
   constexpr int kAOff = HALO ? kHaloBytes : kABytes;  // offset of the weight tile(s) inside a stage
@@ -354,12 +359,12 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   constexpr uint32_t kAccStride = acc_stride_for<BN>();
   constexpr uint32_t kTmemCols = 2 * kAccStride;
   uint8_t* staging = smem + STAGES * kStageBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + (DS ? 2 : 1) * kStagingBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
-  uint64_t* res_bar = tmem_empty_bar + 2;        // [2] residual tile landed (one per epilogue group)
-  uint64_t* b_full = res_bar + 2;                // weight-stationary mode: resident weight tile landed
+  uint64_t* res_bar = tmem_empty_bar + 2;        // [2 groups][2 slabs] residual tile landed (single slab: [g] only)
+  uint64_t* b_full = res_bar + 4;                // weight-stationary mode: resident weight tile landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -384,6 +389,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       mbar_init(&tmem_full_bar[b], 1);
       mbar_init(&tmem_empty_bar[b], TWO ? 16 : 8);  // one arrive per epilogue warp (of both CTAs in pair mode)
       mbar_init(&res_bar[b], 1);
+      mbar_init(&res_bar[2 + b], 1);
     }
     mbar_init(b_full, 1);
     fence_mbar_init();
@@ -561,7 +567,22 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     const int my_chunks = (NCHUNK - g + 1) / 2;  // chunks g, g+2, ...
     uint32_t res_phase = 0;
     int local = 0;
+    // DS: request the residual tile of `tile_` into staging slab `slab_` (barrier index 2 * slab_ + g)
+    auto request_res = [&](int tile_, int slab_) {
+      const int ntile_ = tile_ % n_tiles;
+      const int mtile_ = (tile_ / n_tiles) * CS + crank;
+      const int w0_ = (mtile_ % p.tiles_w) * p.bw, h0_ = ((mtile_ / p.tiles_w) % p.tiles_h) * p.bh;
+      const int n0_ = mtile_ < p.tiles_w * p.tiles_h * p.tiles_g ? (mtile_ / (p.tiles_w * p.tiles_h)) * p.bn : p.NI;
+      mbar_expect_tx(&res_bar[2 * slab_ + g], my_chunks * kChunkBytes);
+      for (int chunk = g; chunk < NCHUNK; chunk += 2)
+        tma_load_4d(staging + slab_ * kStagingBytes + chunk * kChunkBytes, &tmR, &res_bar[2 * slab_ + g],
+                    ntile_ * OUT_W + chunk * CW, w0_, h0_, n0_);
+    };
+    if constexpr (DS) {
+      if (issuer && has_res && my_chunks > 0 && tile_first < total_tiles) request_res(tile_first, 0);
+    }
     for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++local) {
+      uint8_t* const slab = staging + (DS ? (local & 1) * kStagingBytes : 0);
       const int ntile = tile % n_tiles;
       const int mtile = (tile / n_tiles) * CS + crank;
       const int tw = mtile % p.tiles_w;
@@ -580,9 +601,13 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         if (issuer) {
           bulk_wait_group_read<0>();
           if (has_res && my_chunks > 0) {
-            mbar_expect_tx(&res_bar[g], my_chunks * kChunkBytes);
-            for (int chunk = g; chunk < NCHUNK; chunk += 2)
-              tma_load_4d(staging + chunk * kChunkBytes, &tmR, &res_bar[g], ntile * OUT_W + chunk * CW, w0, h0, n0);
+            if constexpr (DS) {  // the other slab is free now (its store has been read): fetch the NEXT tile's residual
+              if (tile + tile_step < total_tiles) request_res(tile + tile_step, (local + 1) & 1);
+            } else {
+              mbar_expect_tx(&res_bar[g], my_chunks * kChunkBytes);
+              for (int chunk = g; chunk < NCHUNK; chunk += 2)
+                tma_load_4d(staging + chunk * kChunkBytes, &tmR, &res_bar[g], ntile * OUT_W + chunk * CW, w0, h0, n0);
+            }
           }
         }
         if (!has_res) named_bar_sync(1 + g, 128);
@@ -591,14 +616,18 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       tc_fence_after();
       if constexpr (TILEWIDE) {
         if (has_res && my_chunks > 0) {
-          mbar_wait(&res_bar[g], res_phase);
-          res_phase ^= 1;
+          if constexpr (DS) {
+            mbar_wait(&res_bar[2 * (local & 1) + g], (local >> 1) & 1);
+          } else {
+            mbar_wait(&res_bar[g], res_phase);
+            res_phase ^= 1;
+          }
         }
       }
       const uint32_t taddr = tmem_base + buf * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
       for (int chunk = g; chunk < NCHUNK; chunk += 2) {
-        uint8_t* stg = TILEWIDE ? staging + chunk * kChunkBytes : staging + g * kChunkBytes;
+        uint8_t* stg = TILEWIDE ? slab + chunk * kChunkBytes : staging + g * kChunkBytes;
         const int c0 = chunk * CW;             // column inside the tile's output window
         const int ocol0 = ntile * OUT_W + c0;  // global output column
         if constexpr (!TILEWIDE) {
@@ -725,7 +754,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         named_bar_sync(1 + g, 128);
         if (issuer && p.dbg_skip != 3) {
           for (int chunk = g; chunk < NCHUNK; chunk += 2)
-            tma_store_4d(&tmD, staging + chunk * kChunkBytes, ntile * OUT_W + chunk * CW, w0, h0, n0);
+            tma_store_4d(&tmD, slab + chunk * kChunkBytes, ntile * OUT_W + chunk * CW, w0, h0, n0);
           bulk_commit_group();
         }
       }
@@ -797,13 +826,14 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, int CS, bool TWO = false, bool HALO = false>
+template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, int CS, bool TWO = false, bool HALO = false,
+          bool DS = false>
 static int launch_persistent_cs(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                                 const CUtensorMap& tmR, const GemmKParams& kp, int m_tiles, int n_tiles,
                                 cudaStream_t stream) {
-  constexpr int smem = persist_smem_bytes<BN, STAGES, CW, GEGLU, TILEWIDE, TWO, HALO>();
+  constexpr int smem = persist_smem_bytes<BN, STAGES, CW, GEGLU, TILEWIDE, TWO, HALO, DS>();
   static_assert(smem <= 227 * 1024, "persistent GEMM configuration exceeds shared memory");
-  auto kern = gemm_tc_persistent_kernel<BN, STAGES, CW, GEGLU, TILEWIDE, CS, TWO, HALO>;
+  auto kern = gemm_tc_persistent_kernel<BN, STAGES, CW, GEGLU, TILEWIDE, CS, TWO, HALO, DS>;
   static bool configured = false;
   if (!configured) {
     IVV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -968,6 +998,14 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
       if (v == 32 || v == 64 || v == 128 || v == 160 || v == 256) bn_sel = v;
     }
   }
+  // Residual GEMMs with short main loops (the attention / temporal out-projections, K = 320 and 640): pair kernel with
+  // two staging slabs and 160-wide tiles, so the residual fetch of the next tile overlaps this tile's epilogue.
+  // IVV_DS=0 disables (tuning hook).
+  const bool ds = a->residual != nullptr && !halo && !a->geglu && a->taps == 1 && a->c <= 640 && (a->n_out % 160) == 0 &&
+                  persistent_ok && m_tiles >= 2 && !(getenv("IVV_DS") && atoi(getenv("IVV_DS")) == 0) &&
+                  !(getenv("IVV_PAIR") && atoi(getenv("IVV_PAIR")) == 0) && getenv("IVV_CLUSTER") == nullptr &&
+                  getenv("IVV_FORCE_BN") == nullptr;
+  if (ds) bn_sel = 160;
   const int n_tiles = (int)((a->n_out + bn_sel - 1) / bn_sel);
 
   // ---- tensor maps ----
@@ -1026,6 +1064,10 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
     // CTA pairs (tcgen05.mma.cta_group::2, M = 256): default whenever there are at least two M tiles
     bool pair = m_tiles >= 2 && kp.ws_stages == 0;
     if (const char* f = getenv("IVV_PAIR")) pair = pair && atoi(f) != 0;
+    if (ds) {
+      kp.ws_stages = 0;
+      return launch_persistent_cs<160, 5, 32, false, true, 2, true, false, true>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
+    }
     if (halo) {
       // stage = 20 KB activation box + 3 half weight tiles; ring staging where the main loop (>= 15 iterations of 12
       // MMAs) hides the epilogue anyway

@@ -13,6 +13,42 @@ namespace ivv {
 constexpr int kTPad = 8;       // halfs of row padding: 16-byte reads of consecutive frames hit distinct banks
 constexpr int kMaxFrames = 32;
 
+// 16-byte asynchronous global -> shared copy (LDGSTS); src_bytes = 0 zero-fills the destination. The gather of a
+// sequence is 16 x 3 scattered row segments: issued as plain load/store pairs each thread waits for one HBM round trip
+// per vector (7-30 of them in a row); as cp.async they are all in flight at once.
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// Walk over the (frame, vector) grid of a gather / scatter -- nf frame rows of J 16-byte vectors -- without per-vector
+// index arithmetic: a thread keeps its vector column j and strides over frames (R = blockDim / J rows per pass; when a
+// row is longer than the CTA, several columns per thread), so the inner loop is one copy plus two pointer increments.
+// fn(f, j, g, sm): g / sm = offsets in halfs into the global tensor (frame stride gs) and the shared tile (row stride ss).
+// The straightforward i / J, i % J form with 64-bit row products spent ~75 instructions per vector and made the kernel
+// issue-bound (2.4 TB/s at the 32x48 level).
+template <class Fn>
+__device__ __forceinline__ void walk_rows(int J, int nf, long long gs, int ss, Fn&& fn) {
+  const int nt = blockDim.x, tid = threadIdx.x;
+  int R = 1, f0 = 0, j0 = tid, jstep = nt;
+  if (nt >= J) {
+    R = nt / J;
+    f0 = tid / J;
+    j0 = tid - f0 * J;
+    jstep = J;  // one column per thread
+    if (f0 >= R) return;
+  }
+  const long long dg = R * gs;
+  const int dsm = R * ss;
+  for (int j = j0; j < J; j += jstep) {
+    long long g = f0 * gs + j * 8;
+    int sm = f0 * ss + j * 8;
+#pragma unroll 4
+    for (int f = f0; f < nf; f += R, g += dg, sm += dsm) fn(f, j, g, sm);
+  }
+}
+
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
@@ -37,15 +73,17 @@ __global__ void temporal_attn_kernel(const __half* __restrict__ qkv, __half* __r
 
   // ---- gather: frames x 3 segments of seg halfs (16-byte vectors, coalesced per frame row) ----
   const int vec_per_seg = seg / 8;
-  const int total_vec = frames * 3 * vec_per_seg;
-  for (int i = threadIdx.x; i < total_vec; i += blockDim.x) {
-    const int v = i % vec_per_seg;
-    const int part = (i / vec_per_seg) % 3;
-    const int f = i / (3 * vec_per_seg);
-    const long long row = (clip * frames + f) * hw + pix;
-    const uint4 u = *reinterpret_cast<const uint4*>(qkv + row * 3 * C + (long long)part * C + head0 * d + v * 8);
-    *reinterpret_cast<uint4*>(s + f * row_ld + part * seg + v * 8) = u;
+  {
+    // vector j of a frame row: part = j / vec_per_seg (q, k or v); source column part * C + head0 * d + (j - part * vps) * 8,
+    // shared-memory column j * 8
+    const __half* src0 = qkv + ((clip * frames) * hw + pix) * 3 * C + head0 * d;
+    const long long fstride = hw * 3 * (long long)C;
+    walk_rows(3 * vec_per_seg, frames, fstride, row_ld, [&](int, int j, long long g, int sm) {
+      const int part = (j >= vec_per_seg) + (j >= 2 * vec_per_seg);
+      cp_async16(s + sm, src0 + g + part * (C - seg), 16);
+    });
   }
+  cp_async_wait_all();
   __syncthreads();
 
   const int hl = threadIdx.x / frames;  // local head
@@ -105,12 +143,12 @@ __global__ void temporal_attn_kernel(const __half* __restrict__ qkv, __half* __r
   }
   __syncthreads();
   // ---- coalesced write-out of the seg-wide output rows ----
-  const int total_out = frames * vec_per_seg;
-  for (int i = threadIdx.x; i < total_out; i += blockDim.x) {
-    const int v = i % vec_per_seg;
-    const int f = i / vec_per_seg;
-    const long long row = (clip * frames + f) * hw + pix;
-    *reinterpret_cast<uint4*>(o + row * C + head0 * d + v * 8) = *reinterpret_cast<const uint4*>(s + f * row_ld + v * 8);
+  {
+    __half* dst0 = o + ((clip * frames) * hw + pix) * C + head0 * d;
+    const long long fstride = hw * (long long)C;
+    walk_rows(vec_per_seg, frames, fstride, row_ld, [&](int, int, long long g, int sm) {
+      *reinterpret_cast<uint4*>(dst0 + g) = *reinterpret_cast<const uint4*>(s + sm);
+    });
   }
 }
 
@@ -146,18 +184,16 @@ __global__ void temporal_attn_mma_kernel(const __half* __restrict__ qkv, __half*
   const long long clip = bp / hw, pix = bp % hw;
   const int head0 = blockIdx.y * heads_per_cta;
   const int vec_per_seg = seg / 8;
-  const int total_vec = 16 * 3 * vec_per_seg;  // rows >= frames are zero-filled
-  for (int i = threadIdx.x; i < total_vec; i += blockDim.x) {
-    const int v = i % vec_per_seg;
-    const int part = (i / vec_per_seg) % 3;
-    const int f = i / (3 * vec_per_seg);
-    uint4 u = make_uint4(0, 0, 0, 0);
-    if (f < frames) {
-      const long long row = (clip * frames + f) * hw + pix;
-      u = *reinterpret_cast<const uint4*>(qkv + row * 3 * C + (long long)part * C + head0 * d + v * 8);
-    }
-    *reinterpret_cast<uint4*>(s + f * row_ld + part * seg + v * 8) = u;
+  {
+    const __half* src0 = qkv + ((clip * frames) * hw + pix) * 3 * C + head0 * d;
+    const long long fstride = hw * 3 * (long long)C;
+    walk_rows(3 * vec_per_seg, 16, fstride, row_ld, [&](int f, int j, long long g, int sm) {
+      const int part = (j >= vec_per_seg) + (j >= 2 * vec_per_seg);
+      const bool in = f < frames;  // rows >= frames are zero-filled: valid address (frame 0), zero bytes read
+      cp_async16(s + sm, in ? src0 + g + part * (C - seg) : src0, in ? 16 : 0);
+    });
   }
+  cp_async_wait_all();
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp < heads_per_cta) {
@@ -245,12 +281,12 @@ __global__ void temporal_attn_mma_kernel(const __half* __restrict__ qkv, __half*
     }
   }
   __syncthreads();
-  const int total_out = frames * vec_per_seg;
-  for (int i = threadIdx.x; i < total_out; i += blockDim.x) {
-    const int v = i % vec_per_seg;
-    const int f = i / vec_per_seg;
-    const long long row = (clip * frames + f) * hw + pix;
-    *reinterpret_cast<uint4*>(o + row * C + head0 * d + v * 8) = *reinterpret_cast<const uint4*>(s + f * row_ld + v * 8);
+  {
+    __half* dst0 = o + ((clip * frames) * hw + pix) * C + head0 * d;
+    const long long fstride = hw * (long long)C;
+    walk_rows(vec_per_seg, frames, fstride, row_ld, [&](int, int, long long g, int sm) {
+      *reinterpret_cast<uint4*>(dst0 + g) = *reinterpret_cast<const uint4*>(s + sm);
+    });
   }
 }
 

@@ -46,7 +46,9 @@ def h16(*shape, scale=1.0, seed=0):
 # ------------------------------------------------------------------------------------------------ GEMM / linear
 @pytest.mark.parametrize("rows,k,n", [(128, 64, 128), (300, 320, 320), (1000, 1280, 640), (77 * 3, 768, 2560),
                                       (3, 320, 1280), (4608, 2560, 1280), (130, 72, 40),
-                                      (73728, 320, 320), (40000, 320, 960), (50000, 256, 128)])  # weight-stationary
+                                      # short-K residual GEMMs: double staging slab (K <= 640, N % 160 == 0)
+                                      (73728, 320, 320), (40000, 320, 960), (18432, 640, 640), (1000, 640, 320),
+                                      (50000, 256, 128)])
 def test_linear(rows, k, n):
     ops = _ops()
     x = h16(rows, k, seed=1)
@@ -56,6 +58,20 @@ def test_linear(rows, k, n):
     out = ops.linear(x, ops.pack_linear(w), bias=b, residual=res)
     ref = x.float() @ w.float().t() + b.float() + res.float()
     report(f"linear {rows}x{k}x{n}", out, ref)
+
+
+@pytest.mark.parametrize("rows,k,n", [(73728, 320, 320), (40000, 320, 960), (50000, 256, 128), (18432, 640, 1920),
+                                      (300, 320, 320)])
+def test_linear_no_residual(rows, k, n):
+    """Same GEMMs without the residual term: the weight-stationary mode (short K, many row tiles) and the plain pair
+    kernel."""
+    ops = _ops()
+    x = h16(rows, k, seed=1)
+    w = h16(n, k, scale=k ** -0.5, seed=2)
+    b = h16(n, seed=3)
+    out = ops.linear(x, ops.pack_linear(w), bias=b)
+    ref = x.float() @ w.float().t() + b.float()
+    report(f"linear (no residual) {rows}x{k}x{n}", out, ref)
 
 
 def test_linear_geglu():
@@ -374,6 +390,13 @@ out = ops.conv3x3(fr(x), ops.pack_conv3x3(wt), n, h, w, bias=b, residual=fr(res)
 ref = torch.nn.functional.conv2d(x.double(), wt.double(), b.double(), padding=1) + res.double()
 err = (out.reshape(n, h, w, co).permute(0, 3, 1, 2).double() - ref).abs()
 assert (err <= 1e-4 + 1e-3 * ref.abs()).all(), float(err.max())
+# short-K linear + residual (double staging slab / weight-stationary / single-slab variants)
+rows, c = 128 * 37 + 50, 320
+xl = torch.randn(rows, c, device=dev).half(); wl = (torch.randn(c, c, device=dev) * c ** -0.5).half()
+bl = torch.randn(c, device=dev).half(); rl = torch.randn(rows, c, device=dev).half()
+o = ops.linear(xl, ops.pack_linear(wl), bias=bl, residual=rl)
+refl = xl.double() @ wl.double().t() + bl.double() + rl.double()
+assert ((o.double() - refl).abs() <= 1e-4 + 1e-3 * refl.abs()).all()
 # odd number of M tiles (ghost tile of a CTA pair) and GEGLU
 rows, c = 128 * 5, 320
 xl = torch.randn(rows, c, device=dev).half(); wl = (torch.randn(8 * c, c, device=dev) * c ** -0.5).half()
@@ -400,7 +423,8 @@ print("variant ok")
                                  {"IVV_ATTN_MODE": "1"}, {"IVV_ATTN_MODE": "2"}, {"IVV_ATTN_POLY": "1"},
                                  {"IVV_ATTN_PAIR_SHORT": "0"},
                                  {"IVV_ATTN_MODE": "0", "IVV_ATTN_POLY": "1"},
-                                 {"IVV_FORCE_BN": "128"}, {"IVV_FORCE_BN": "256"}, {"IVV_HALO": "0"}])
+                                 {"IVV_FORCE_BN": "128"}, {"IVV_FORCE_BN": "256"}, {"IVV_HALO": "0"}, {"IVV_DS": "0"},
+                                 {"IVV_DS": "0", "IVV_NO_WS": "1"}])
 def test_kernel_variants(env):
     """The opt-in / fallback code paths (single-CTA GEMM, multicast clusters, two-tile attention, other tile widths)
     stay correct: same checks in a subprocess with the tuning environment variables set."""

@@ -21,6 +21,8 @@ SHAPES = [
     (1, 1, 73728, 1280, 320, 1, True), (1, 1, 18432, 2560, 640, 1, True), (1, 1, 1152, 1280, 1280, 1, True),
 ]
 SETTINGS = [dict(IVV_HALO="0"), dict(IVV_HALO="1")]
+# temporal attention (clips, frames, pixels, channels): the four UNet levels
+TATTN = [(3, 16, 1536, 320), (3, 16, 384, 640), (3, 16, 96, 1280), (3, 16, 24, 1280)]
 
 
 def child():
@@ -58,10 +60,31 @@ def child():
               f"{tf:7.1f} TFLOP/s", flush=True)
 
 
+    for clips, frames, hw, c in TATTN:
+        rows = clips * frames * hw
+        nbuf = max(2, min(8, int(3e8 // (rows * 4 * c * 2)) + 1))
+        qs = [torch.randn(rows, 3 * c, device=dev).half() for _ in range(nbuf)]
+        os_ = [torch.empty(rows, c, device=dev, dtype=torch.float16) for _ in range(nbuf)]
+        for i in range(nbuf):
+            ops.temporal_attention(qs[i], clips, frames, hw, c, 8, out=os_[i])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(40):
+            ops.temporal_attention(qs[i % nbuf], clips, frames, hw, c, 8, out=os_[i % nbuf])
+        e1.record()
+        torch.cuda.synchronize()
+        us = 1e3 * e0.elapsed_time(e1) / 40
+        print(f"[{tag:22s}] temporal attention rows={rows:6d} c={c:5d}: {us:8.1f} us {8.0 * rows * c / us / 1e3:8.0f} GB/s",
+              flush=True)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1:
+    if len(sys.argv) > 1 and sys.argv[1] == "child":
         child()
     else:
-        for st in SETTINGS:
-            env = {k: v for k, v in os.environ.items() if k != "IVV_HALO"}
+        # extra settings: each argument is a comma-separated KEY=VALUE list, e.g.  IVV_DS=0  IVV_DS=1
+        settings = SETTINGS if len(sys.argv) == 1 else [dict(kv.split("=") for kv in a.split(",")) for a in sys.argv[1:]]
+        for st in settings:
+            env = {k: v for k, v in os.environ.items() if k not in st}
             subprocess.run([sys.executable, __file__, "child"], env=dict(env, **st))
