@@ -72,7 +72,9 @@ int ivv_im2col_s2(const void* x, void* out, int64_t n_img, int64_t h, int64_t w,
 /* ---- K6/K7: GroupNorm (+SiLU) ------------------------------------------------------------------------------
  * Replaces torch.nn.GroupNorm + F.silu at resnet.py:177-178,188-194, unet.py:427-428 (5-D: statistics span
  * frames_per_group = F frames) and attention.py:101, motion_module.py:136, vqvae/model.py:31-32 (per frame: 1).
- * x,y: fp16 [n_img, hw, c]; stats workspace: ivv_groupnorm_ws_bytes() bytes, 16-byte aligned, (re)initialised by the call. */
+ * x,y: fp16 [n_img, hw, c]; stats workspace: ivv_groupnorm_ws_bytes() bytes, 16-byte aligned. Its first 4096 bytes (the
+ * CTA ticket counters) must be ZERO the first time the buffer is used; every call returns them to zero, so one
+ * zero-filled buffer serves any number of calls on a stream (no memset in front of each norm).                    */
 int ivv_groupnorm(const void* x, void* y, const void* gamma, const void* beta, int64_t n_img, int64_t hw, int64_t c,
                   int32_t groups, int64_t frames_per_group, float eps, int32_t silu, void* stats_ws,
                   size_t stats_ws_bytes, ivv_stream_t stream);

@@ -11,7 +11,9 @@ namespace ivv {
 //   x: [n_bg, rows_per_bg, C]; a thread owns one 8-channel vector column and strides over rows (4 loads in flight).
 //   Deterministic: per-CTA partials are reduced in a fixed order inside the CTA, written to the workspace, and the
 //   LAST CTA of each batch-group (atomic ticket) sums them in chunk order in double precision.
-// workspace: [counters u32 x n_bg (256-B padded)] [final float2 x n_bg x G] [partials float2 x n_bg x max_chunks x G]
+// workspace: [counters u32 x n_bg (>= 4 KB)] [final float2 x n_bg x G] [partials float2 x n_bg x max_chunks x G]
+// The ticket counters wrap back to zero by themselves (atomicInc with the chunk count as the limit), so a workspace
+// that was zero when first used stays usable call after call without a memset node in front of every norm.
 // ------------------------------------------------------------------------------------------------
 struct GnWs {
   unsigned int* counters;
@@ -20,11 +22,15 @@ struct GnWs {
   int max_chunks;
 };
 __host__ __device__ inline int gn_max_chunks(long long n_bg) { return (int)(148 * 4 / n_bg) + 2; }
-__host__ __device__ inline size_t gn_counter_bytes(long long n_bg) { return (size_t)((n_bg * 4 + 255) / 256 * 256); }
+constexpr long long kGnSelfCleanBytes = 4096;  // counter region the caller zero-fills once (n_bg <= 1024)
+__host__ __device__ inline size_t gn_counter_bytes(long long n_bg) {
+  const long long b = (n_bg * 4 + 255) / 256 * 256;
+  return (size_t)(b < kGnSelfCleanBytes ? kGnSelfCleanBytes : b);
+}
 
 __global__ void gn_stats_kernel(const __half* __restrict__ x, GnWs ws, long long rows_per_bg, int C, int groups,
                                 long long rows_per_cta, int V, int R, float eps) {
-  extern __shared__ float s_part[];  // [R][C][2]
+  extern __shared__ __align__(16) float s_part[];  // [R][C][2]
   __shared__ bool s_last;
   griddep_sync();
   const int bg = blockIdx.y;
@@ -89,24 +95,56 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, GnWs ws, long long
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned int t = atomicAdd(&ws.counters[bg], 1u);
+    const unsigned int t = atomicInc(&ws.counters[bg], (unsigned int)chunks - 1);  // wraps to 0 on the last ticket
     s_last = (t == (unsigned int)chunks - 1);
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // Final merge by the last CTA, still in a fixed order (bit-reproducible), but spread over the whole CTA: L lanes per
+  // group each sum every L-th chunk, then one thread per group adds the L lane sums in lane order. A single thread per
+  // group walking ~200 chunks (5-D norms: 3 batch groups x 199 chunks) was a ~15 us serial tail of L2 round trips.
+  const int L = (int)blockDim.x / groups;
+  const double inv_n = 1.0 / ((double)rows_per_bg * cpg);
+  auto finish = [&](int g, double a, double b) {
+    const double mean = a * inv_n;
+    double var = b * inv_n - mean * mean;
+    if (var < 0) var = 0;
+    ws.final_[(long long)bg * groups + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+  };
+  if (L >= 2) {
+    double2* s_lane = reinterpret_cast<double2*>(s_part);  // [L][groups]; the row partials are no longer needed
+    const int g = threadIdx.x % groups, l = threadIdx.x / groups;
+    if (l < L) {
+      double a = 0.0, b = 0.0;
+#pragma unroll 4
+      for (int ch = l; ch < chunks; ch += L) {
+        const float2 pv = __ldcg(&ws.partial[((long long)bg * ws.max_chunks + ch) * groups + g]);
+        a += (double)pv.x;
+        b += (double)pv.y;
+      }
+      s_lane[l * groups + g] = make_double2(a, b);
+    }
+    __syncthreads();
+    if (threadIdx.x < groups) {
+      double a = 0.0, b = 0.0;
+      for (int ll = 0; ll < L; ++ll) {
+        a += s_lane[ll * groups + threadIdx.x].x;
+        b += s_lane[ll * groups + threadIdx.x].y;
+      }
+      finish(threadIdx.x, a, b);
+    }
+    return;
+  }
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     double a = 0.0, b = 0.0;
+#pragma unroll 4
     for (int ch = 0; ch < chunks; ++ch) {
       const float2 pv = __ldcg(&ws.partial[((long long)bg * ws.max_chunks + ch) * groups + g]);
       a += (double)pv.x;
       b += (double)pv.y;
     }
-    const double inv_n = 1.0 / ((double)rows_per_bg * cpg);
-    const double mean = a * inv_n;
-    double var = b * inv_n - mean * mean;
-    if (var < 0) var = 0;
-    ws.final_[(long long)bg * groups + g] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    finish(g, a, b);
   }
 }
 
@@ -335,7 +373,8 @@ static int groupnorm_impl(const void* x, void* y, const void* gamma, const void*
   ws.final_ = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(stats_ws) + gn_counter_bytes(n_bg));
   ws.partial = ws.final_ + n_bg * groups;
   ws.max_chunks = gn_max_chunks(n_bg);
-  IVV_CHECK_CUDA(cudaMemsetAsync(stats_ws, 0, gn_counter_bytes(n_bg), stream));
+  // more batch groups than the self-cleaning region covers: counters beyond it may alias older final/partial data
+  if (n_bg * 4 > kGnSelfCleanBytes) IVV_CHECK_CUDA(cudaMemsetAsync(stats_ws, 0, gn_counter_bytes(n_bg), stream));
   const int V = (int)(c / 8);
   const int R = V >= 256 ? 1 : 256 / V;
   const int threads = V * R;

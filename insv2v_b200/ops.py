@@ -230,7 +230,8 @@ def _gn_ws(nbytes, device):
     key = (device, torch.cuda.current_stream().cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        # zero-filled once: the kernels return the ticket counters at its head to zero after every call (ivv.h K6/K7)
+        ws = torch.zeros(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
         _ws_cache[key] = ws
     return ws
 

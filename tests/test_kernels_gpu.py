@@ -295,6 +295,12 @@ def test_layout_roundtrip_and_glue():
     assert torch.equal(_nchw(up, 3, ho, wo), F.interpolate(img.float(), scale_factor=2.0, mode="nearest").half())
     up2, ho, wo = ops.upsample_nearest(_frames(img), 3, 5, 7, 9, 15)
     assert torch.equal(_nchw(up2, 3, 9, 15), F.interpolate(img.float(), size=(9, 15), mode="nearest").half())
+    # rows longer than a CTA (several vector columns per thread) and a ragged last row chunk
+    a2, b2 = h16(77, 1280, seed=4), h16(77, 1536, seed=5)
+    assert torch.equal(ops.concat_channels(a2, b2), torch.cat([a2, b2], dim=1))
+    img2 = h16(2, 2304, 3, 4, seed=6)
+    up3, ho, wo = ops.upsample_nearest(_frames(img2), 2, 3, 4)
+    assert torch.equal(_nchw(up3, 2, ho, wo), F.interpolate(img2.float(), scale_factor=2.0, mode="nearest").half())
     report("silu", ops.silu(a), F.silu(a.float()))
     report("scale", ops.scale(a, 1 / 0.18215), a.float() / 0.18215)
 
