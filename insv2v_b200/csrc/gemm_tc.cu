@@ -30,7 +30,9 @@ struct GemmKParams {
   long long split_stride;         // elements between the fp32 partial planes
   int ws_stages;                  // >0: weight-stationary mode (persistent kernel): the CTA's weight tile (all of K) is
                                   // loaded once and stays in shared memory; only A tiles stream through ws_stages slots
-  int dbg_skip;                   // tuning only (IVV_DEBUG_SKIP): 1 = no MMA issue, 2 = no TMA loads (results are garbage)
+  int dbg_skip;                   // tuning only (IVV_DEBUG_SKIP): 1 = no MMA issue, 2 = no TMA loads, 3 = no TMA store,
+                                  // 4 = no residual term, 5 = no epilogue work (results are garbage)
+  long long* trace;               // tuning only (ivv_debug_gemm_trace): clock64 stamps of CTA 0, [tile][16]
   int halo_bytes;                 // HALO kernels: bytes of one (bw x (bh + 2)) activation box = (bh + 2) * bw * 128
   void* d;
   long long d_ld;
@@ -402,6 +404,13 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   griddep_sync();  // PDL: everything above overlapped the previous kernel's tail
+  // tuning trace (tools/gemm_trace.py): slots 0-1 producer (first / last load of the tile issued), 2-3 MMA thread
+  // (accumulator free, tile committed), 4-11 epilogue group 0 (top, store drained, accumulator seen, residual seen,
+  // last chunk done, group barrier, store issued)
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+  auto stamp = [&](int t_, int slot) {
+    if (tracing && t_ < 32) p.trace[t_ * 16 + slot] = clock64();
+  };
 
   if (warp == 0) {
     if (role_elect()) {  // elect.sync, not lane == 0: see gemm_tc_kernel
@@ -416,7 +425,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           tma_load_3d(b_res + it * (BN * 128), &tmB, b_full, (it - tap * p.kblocks) * kBlockK, ntile0 * BN, tap);
         }
       }
-      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+      int plocal = 0;
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++plocal) {
         const int ntile = tile % n_tiles;
         const int mtile = (tile / n_tiles) * CS + crank;
         const int tw = mtile % p.tiles_w;
@@ -425,6 +435,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         const int w0 = tw * p.bw, h0 = th * p.bh;
       const int n0 = mtile < p.tiles_w * p.tiles_h * p.tiles_g ? tg * p.bn : p.NI;  // ghost tile of an odd cluster: fully out of bounds
         for (int it = 0; it < its_per_tile; ++it) {
+          if (it == 0 || it == its_per_tile - 1) stamp(plocal, it == 0 ? 0 : 1);
           const int tap = it / p.kblocks;
           const int kb = it - tap * p.kblocks;
           int dy = 0, dx = 0;
@@ -506,6 +517,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         const int buf = local & 1;
         mbar_wait(&tmem_empty_bar[buf], ((local >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
+        stamp(local, 2);
         const uint32_t tacc = tmem_base + buf * kAccStride;
         for (int it = 0; it < its_per_tile; ++it) {
           mbar_wait(&full_bar[stage], phase);
@@ -544,6 +556,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           }
         }
         if constexpr (TWO) umma_commit_2sm(&tmem_full_bar[buf], kMask); else umma_commit(&tmem_full_bar[buf]);
+        stamp(local, 3);
       }
     }
   } else {
@@ -563,7 +576,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       if constexpr (TWO) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[buf_]), 0));
       else mbar_arrive(&tmem_empty_bar[buf_]);
     };
-    const bool has_res = !GEGLU && p.residual != nullptr;
+    const bool has_res = !GEGLU && p.residual != nullptr && p.dbg_skip != 4;  // dbg_skip 4: residual term dropped
     const int my_chunks = (NCHUNK - g + 1) / 2;  // chunks g, g+2, ...
     uint32_t res_phase = 0;
     int local = 0;
@@ -595,15 +608,20 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       const long long pix = (static_cast<long long>(n) * p.H + h) * p.W + w;
       const __half* rb = (p.rowbias && valid) ? p.rowbias + (pix / p.rowbias_group) * p.rowbias_ld : nullptr;
       const int buf = local & 1;
+      const bool etr = issuer && g == 0;
+      if (etr) stamp(local, 4);
       if constexpr (TILEWIDE) {
         // While the main loop of this tile is still running: make sure the stores of the previous tile have drained
         // the staging slabs, then let TMA drop the residual tile straight into them (coalesced, no registers).
         if (issuer) {
-          bulk_wait_group_read<0>();
-          if (has_res && my_chunks > 0) {
-            if constexpr (DS) {  // the other slab is free now (its store has been read): fetch the NEXT tile's residual
-              if (tile + tile_step < total_tiles) request_res(tile + tile_step, (local + 1) & 1);
-            } else {
+          if constexpr (DS) {
+            // residual GEMM: this tile's slab was refilled by the residual fetch, which already waited for its store;
+            // the drain of the PREVIOUS tile's store (it sits behind the producer's loads in the TMA queue: ~1 100 clk
+            // in the trace) is waited for after the first chunk, where it has long finished
+            if (!has_res) bulk_wait_group_read<0>();
+          } else {
+            bulk_wait_group_read<0>();
+            if (has_res && my_chunks > 0) {
               mbar_expect_tx(&res_bar[g], my_chunks * kChunkBytes);
               for (int chunk = g; chunk < NCHUNK; chunk += 2)
                 tma_load_4d(staging + chunk * kChunkBytes, &tmR, &res_bar[g], ntile * OUT_W + chunk * CW, w0, h0, n0);
@@ -612,8 +630,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         }
         if (!has_res) named_bar_sync(1 + g, 128);
       }
+      if (etr) stamp(local, 5);
       mbar_wait(&tmem_full_bar[buf], (local >> 1) & 1);
       tc_fence_after();
+      if (etr) stamp(local, 6);
       if constexpr (TILEWIDE) {
         if (has_res && my_chunks > 0) {
           if constexpr (DS) {
@@ -624,7 +644,13 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           }
         }
       }
+      if (etr) stamp(local, 7);
       const uint32_t taddr = tmem_base + buf * kAccStride + (static_cast<uint32_t>(q * 32) << 16);
+      if (p.dbg_skip == 5) {  // tuning only: no epilogue work at all (accumulator handed straight back, nothing stored)
+        tc_fence_before();
+        if (lane == 0) release_acc(buf);
+        continue;
+      }
 #pragma unroll 1
       for (int chunk = g; chunk < NCHUNK; chunk += 2) {
         uint8_t* stg = TILEWIDE ? slab + chunk * kChunkBytes : staging + g * kChunkBytes;
@@ -648,6 +674,22 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         }
         float v[CW];
         if constexpr (!GEGLU) {
+          // Bias / per-clip row bias of this chunk as whole 16-byte vectors, requested BEFORE the accumulator is read so
+          // the round trips overlap the TMEM load. (The per-8-column load8h() form compiled into four branchy regions
+          // whose loads could not be hoisted: four serialized L1/L2 round trips, ~1 100 clk per 32-column chunk in the
+          // clock64 trace -- the epilogue, not the main loop, paced every K <= 640 GEMM.)
+          const bool whole = ocol0 + CW <= p.n_out;
+          const bool bias_fast = whole && p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
+          const bool rb_fast = whole && rb != nullptr && (reinterpret_cast<uintptr_t>(rb) & 15) == 0;
+          uint4 bvec[VPR], rvec[VPR];
+          if (bias_fast) {
+#pragma unroll
+            for (int cc = 0; cc < VPR; ++cc) bvec[cc] = __ldg(reinterpret_cast<const uint4*>(p.bias + ocol0) + cc);
+          }
+          if (rb_fast) {
+#pragma unroll
+            for (int cc = 0; cc < VPR; ++cc) rvec[cc] = __ldg(reinterpret_cast<const uint4*>(rb + ocol0) + cc);
+          }
 #pragma unroll
           for (int s = 0; s < CW; s += 32) {
             uint32_t acc[32];
@@ -660,22 +702,28 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             tc_fence_before();
             if (lane == 0) release_acc(buf);
           }
+          auto add_vec = [&](const uint4 (&src)[VPR]) {
 #pragma unroll
-          for (int s = 0; s < CW; s += 8) {
-            const int col = ocol0 + s;
-            if (col < p.n_out) {
-              const int nv = min(8, p.n_out - col);
-              if (p.bias) {
-                float bv[8];
-                load8h(p.bias + col, nv, true, bv);
+            for (int cc = 0; cc < VPR; ++cc) {
+              const __half2* hh = reinterpret_cast<const __half2*>(&src[cc]);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[s + j] += bv[j];
+              for (int t = 0; t < 4; ++t) {
+                const float2 f = __half22float2(hh[t]);
+                v[cc * 8 + 2 * t] += f.x;
+                v[cc * 8 + 2 * t + 1] += f.y;
               }
-              if (rb) {
-                float bv[8];
-                load8h(rb + col, nv, (reinterpret_cast<uintptr_t>(rb + col) & 15) == 0, bv);
+            }
+          };
+          if (bias_fast) add_vec(bvec);
+          if (rb_fast) add_vec(rvec);
+          if ((p.bias != nullptr && !bias_fast) || (rb != nullptr && !rb_fast)) {  // ragged last tile / unaligned vectors
+            const bool bias_slow = p.bias != nullptr && !bias_fast, rb_slow = rb != nullptr && !rb_fast;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[s + j] += bv[j];
+            for (int j = 0; j < CW; ++j) {  // static indices: v must stay in registers
+              const int col = ocol0 + j;
+              if (col < p.n_out) {
+                if (bias_slow) v[j] += __half2float(p.bias[col]);
+                if (rb_slow) v[j] += __half2float(rb[col]);
               }
             }
           }
@@ -740,6 +788,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           }
           *slot = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
+        if constexpr (TILEWIDE && DS) {
+          // first chunk done: the previous tile's store has drained the other slab by now -> fetch the NEXT tile's
+          // residual into it; it has the rest of this tile (two chunks, barrier, store, loop turn) to land
+          if (chunk == g && issuer && has_res) {
+            bulk_wait_group_read<0>();
+            if (tile + tile_step < total_tiles) request_res(tile + tile_step, (local + 1) & 1);
+          }
+        }
         if constexpr (!TILEWIDE) {
           fence_proxy_async_smem();
           named_bar_sync(1 + g, 128);
@@ -750,13 +806,16 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         }
       }
       if constexpr (TILEWIDE) {
+        if (etr) stamp(local, 8);
         fence_proxy_async_smem();
         named_bar_sync(1 + g, 128);
+        if (etr) stamp(local, 9);
         if (issuer && p.dbg_skip != 3) {
           for (int chunk = g; chunk < NCHUNK; chunk += 2)
             tma_store_4d(&tmD, slab + chunk * kChunkBytes, ntile * OUT_W + chunk * CW, w0, h0, n0);
           bulk_commit_group();
         }
+        if (etr) stamp(local, 10);
       }
       if (NCHUNK == 1 && g == 1) {  // this group had no chunk: still release the accumulator
         tc_fence_before();
@@ -895,6 +954,10 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKPar
 
 }  // namespace ivv
 
+static long long* g_gemm_trace = nullptr;
+// tuning only: clock64 trace of CTA 0 of the next persistent-kernel launches into buf ([32 tiles][16] int64); NULL = off
+extern "C" void ivv_debug_gemm_trace(void* buf) { g_gemm_trace = reinterpret_cast<long long*>(buf); }
+
 extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
   using namespace ivv;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
@@ -922,6 +985,7 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
                          !(getenv("IVV_HALO") && atoi(getenv("IVV_HALO")) == 0);
   choose_box(a->w, a->h, a->n_img, want_halo, &kp.bw, &kp.bh, &kp.bn);
   kp.halo_bytes = (kp.bh + 2) * kp.bw * 128;
+  kp.trace = g_gemm_trace;
   kp.tiles_w = (int)((a->w + kp.bw - 1) / kp.bw);
   kp.tiles_h = (int)((a->h + kp.bh - 1) / kp.bh);
   kp.tiles_g = (int)((a->n_img + kp.bn - 1) / kp.bn);

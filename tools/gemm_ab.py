@@ -29,7 +29,10 @@ def child():
     from insv2v_b200 import ops
     dev = torch.device("cuda")
     tag = " ".join(f"{k[4:]}={v}" for k, v in sorted(os.environ.items()) if k.startswith("IVV_"))
+    only = os.environ.get("GEMM_AB_ONLY", "")  # "linear": the 1x1 shapes only, "conv": the 3x3 ones, "none": neither
     for n, h, w, c, n_out, taps, res in SHAPES:
+        if (only == "linear" and taps != 1) or (only == "conv" and taps == 1) or only == "none":
+            continue
         rows = n * h * w
         nbuf = max(2, min(8, int(3e8 // (rows * (c + 2 * n_out) * 2)) + 1))
         xs = [torch.randn(rows, c, device=dev).half() for _ in range(nbuf)]
@@ -60,7 +63,7 @@ def child():
               f"{tf:7.1f} TFLOP/s", flush=True)
 
 
-    for clips, frames, hw, c in TATTN:
+    for clips, frames, hw, c in ([] if only else TATTN):
         rows = clips * frames * hw
         nbuf = max(2, min(8, int(3e8 // (rows * 4 * c * 2)) + 1))
         qs = [torch.randn(rows, 3 * c, device=dev).half() for _ in range(nbuf)]
