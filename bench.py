@@ -150,7 +150,7 @@ def top_gemm_roofline(pk):
     if os.path.exists(tk):  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
         j = json.load(open(tk))
         traffic = j["dram_bytes_read"] + j["dram_bytes_write"]
-    return {"bound": "tensor", "kernel": "gemm_tc_persistent_kernel<160,...> conv3x3 320->320 on [48,32,48] frames",
+    return {"bound": "tensor", "kernel": "gemm_tc_persistent_kernel<160,4,32,...,HALO> conv3x3 320->320 on [48,32,48] frames",
             "achieved": achieved,
             "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"], "traffic": traffic,
             "peak_source": pk["src"] + ", burst (kernel timed alone)", "ms_per_launch": ms,

@@ -406,7 +406,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   griddep_sync();  // PDL: everything above overlapped the previous kernel's tail
   // tuning trace (tools/gemm_trace.py): slots 0-1 producer (first / last load of the tile issued), 2-3 MMA thread
   // (accumulator free, tile committed), 4-11 epilogue group 0 (top, store drained, accumulator seen, residual seen,
-  // last chunk done, group barrier, store issued)
+  // last chunk done, group barrier, store issued; first chunk only: 11 bias requested, 12 accumulator in registers,
+  // 13 bias added, 14 result written to the slab)
   const bool tracing = p.trace != nullptr && blockIdx.x == 0;
   auto stamp = [&](int t_, int slot) {
     if (tracing && t_ < 32) p.trace[t_ * 16 + slot] = clock64();
@@ -690,6 +691,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 #pragma unroll
             for (int cc = 0; cc < VPR; ++cc) rvec[cc] = __ldg(reinterpret_cast<const uint4*>(rb + ocol0) + cc);
           }
+          if (etr && chunk == g) stamp(local, 11);
 #pragma unroll
           for (int s = 0; s < CW; s += 32) {
             uint32_t acc[32];
@@ -698,6 +700,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[s + j] = __uint_as_float(acc[j]);
           }
+          if (etr && chunk == g) stamp(local, 12);
           if (chunk + 2 >= NCHUNK) {  // last chunk of this warp: the accumulator can be handed back to the MMA warp
             tc_fence_before();
             if (lane == 0) release_acc(buf);
@@ -759,6 +762,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             if (lane == 0) release_acc(buf);
           }
         }
+        if (etr && chunk == g) stamp(local, 13);
         // ---- own row of the slab: add the TMA-fetched residual, then overwrite it with the fp16 result ----
         // CW=64: 128-byte rows, SWIZZLE_128B (chunk ^ (row & 7)); CW=32: 64-byte rows, SWIZZLE_64B (chunk ^ ((row>>1)&3))
         uint8_t* srow = stg + r * (CW * 2);
@@ -788,6 +792,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           }
           *slot = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
+        if (etr && chunk == g) stamp(local, 14);
         if constexpr (TILEWIDE && DS) {
           // first chunk done: the previous tile's store has drained the other slab by now -> fetch the NEXT tile's
           // residual into it; it has the rest of this tile (two chunks, barrier, store, loop turn) to land

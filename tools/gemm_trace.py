@@ -39,7 +39,7 @@ L.ivv_debug_gemm_trace(None)
 t = buf.cpu()
 t0 = int(t[t > 0].min())
 names = ["tma:first", "tma:last", "mma:acc ok", "mma:commit", "epi:top", "epi:drained", "epi:acc", "epi:res", "epi:chunks",
-         "epi:bar", "epi:stored"]
+         "epi:bar", "epi:stored", "c0:bias req", "c0:acc regs", "c0:bias add", "c0:written"]
 print(f"rows={rows} k={k} n={n} res={res}  (SM clocks since the first stamp of CTA 0)")
 print("tile " + " ".join(f"{s:>11s}" for s in names))
 for g in range(32):
