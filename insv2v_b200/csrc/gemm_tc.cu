@@ -330,8 +330,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                           const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
                           const __grid_constant__ GemmKParams p, int n_tiles, int total_tiles) {
   // CS > 1: a cluster of CS CTAs works on CS consecutive M tiles of the same N tile; every CTA fetches 1/CS of the
-  // weight tile and TMA-multicasts it to all of them, cutting the L2->SM operand traffic (the measured bound of the
-  // K <= 1280 GEMMs). total_tiles then counts super tiles (M-tile groups x N tiles) and the loop strides by clusters.
+  // weight tile and TMA-multicasts it to all of them (opt-in, measured neutral: the same bytes still enter every SM).
+  // total_tiles then counts super tiles (M-tile groups x N tiles) and the loop strides by clusters.
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   // TWO: the pair runs ONE tcgen05.mma.cta_group::2 (M = 256): each CTA stages its own 128 A rows and only HALF of the
@@ -339,8 +339,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   // HALO (3x3, stride 1, box inside one frame, bw % 8 == 0): the three taps of one filter COLUMN read the same pixels
   // shifted by whole box rows, so ONE (bw x (bh + 2)) box per (dx, 64-channel block) serves all three: the MMA of tap
   // dy starts (dy + 1) * bw rows into the box (a multiple of the 8-row swizzle atom, so the descriptor stays canonical).
-  // Activation bytes per tile drop from 9 x 16 KB to 3 x <= 20 KB per channel block: these GEMMs are bound by the
-  // ~6300 B/clk the L2 can deliver chip-wide, not by the tensor pipe.
+  // Activation bytes per tile drop from 9 x 16 KB to 3 x <= 20 KB per channel block: the main loops fill shared memory
+  // at a near-constant ~40 B/clk per SM, so time follows staged bytes, not tensor-pipe work.
   static_assert(!TWO || CS == 2, "pair MMA needs a 2-CTA cluster");
   static_assert(!HALO || (TWO && !GEGLU), "halo mode is built on the pair kernel");
   // DS (tile-wide staging, residual GEMMs with short main loops): TWO staging slabs used alternately. With one slab the
