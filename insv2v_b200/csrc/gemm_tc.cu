@@ -766,12 +766,23 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         // ---- own row of the slab: add the TMA-fetched residual, then overwrite it with the fp16 result ----
         // CW=64: 128-byte rows, SWIZZLE_128B (chunk ^ (row & 7)); CW=32: 64-byte rows, SWIZZLE_64B (chunk ^ ((row>>1)&3))
         uint8_t* srow = stg + r * (CW * 2);
+        // CW = 32: the four residual vectors of the row are read up front. Read and write of a slot go through the same
+        // shared-memory array, so in the per-slot form below the compiler keeps LDS(cc+1) behind STS(cc) and the pass
+        // becomes four dependent LDS -> FADD -> STS groups (~490 clk per chunk in the clock64 trace).
+        uint4 rpre[CW == 32 ? VPR : 1];
+        if constexpr (CW == 32) {
+          if (has_res) {
+#pragma unroll
+            for (int cc = 0; cc < VPR; ++cc)
+              rpre[cc] = *reinterpret_cast<const uint4*>(srow + ((cc ^ ((r >> 1) & 3)) << 4));
+          }
+        }
 #pragma unroll
         for (int cc = 0; cc < VPR; ++cc) {
           const int sw = (CW == 64) ? (cc ^ (r & 7)) : (cc ^ ((r >> 1) & 3));
           uint4* slot = reinterpret_cast<uint4*>(srow + (sw << 4));
           if (has_res) {
-            const uint4 u = *slot;
+            const uint4 u = (CW == 32) ? rpre[CW == 32 ? cc : 0] : *slot;
             const __half2* hh = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
