@@ -970,6 +970,18 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKPar
 
 }  // namespace ivv
 
+// tuning / test hook (not in ivv.h): the pixel box ivv_gemm picks for a [n_img, h, w] activation, and whether the halo
+// kernel accepts it (box inside one frame, whole swizzle atoms per box row, (bh + 2) * bw <= 160)
+extern "C" int ivv_debug_conv_box(int64_t w, int64_t h, int64_t n_img, int32_t want_halo, int32_t* bw, int32_t* bh,
+                                  int32_t* bn) {
+  int a = 0, b = 0, c = 0;
+  ivv::choose_box(w, h, n_img, want_halo != 0, &a, &b, &c);
+  *bw = a;
+  *bh = b;
+  *bn = c;
+  return ivv::halo_box_ok(a, b, c) ? 1 : 0;
+}
+
 static long long* g_gemm_trace = nullptr;
 // tuning only: clock64 trace of CTA 0 of the next persistent-kernel launches into buf ([32 tiles][16] int64); NULL = off
 extern "C" void ivv_debug_gemm_trace(void* buf) { g_gemm_trace = reinterpret_cast<long long*>(buf); }

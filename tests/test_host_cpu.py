@@ -188,3 +188,37 @@ def test_raftflow_parameter_tree_is_torchvisions():
     assert m.training  # the reference never calls .eval() (inference.py:294)
     with pytest.raises(RuntimeError, match="only on CUDA"):
         m(torch.zeros(1, 3, 128, 128), torch.zeros(1, 3, 128, 128))
+
+
+def test_conv_box_choice_and_halo_eligibility():
+    """Host logic of ivv_gemm: the 128-pixel box of a tile (fewest tiles; for 3x3 convolutions a box the halo kernel
+    takes wins ties) and the halo kernel's eligibility rule. Pure host code: runs without a GPU."""
+    import ctypes
+    from insv2v_b200 import lib
+    L = lib.load()
+    f = L.ivv_debug_conv_box
+    f.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int32] + [ctypes.POINTER(ctypes.c_int32)] * 3
+    f.restype = ctypes.c_int32
+
+    def box(w, h, n, halo):
+        bw, bh, bn = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        ok = f(w, h, n, halo, ctypes.byref(bw), ctypes.byref(bh), ctypes.byref(bn))
+        assert bw.value * bh.value * bn.value == 128
+        return (bw.value, bh.value, bn.value), bool(ok)
+
+    # UNet levels at 256x384: 48x32 and 24x16 latents take halo boxes, 12x8 and 6x4 need several frames per tile
+    assert box(48, 32, 48, 1) == ((16, 8, 1), True)
+    assert box(24, 16, 48, 1) == ((8, 16, 1), True)
+    assert box(12, 8, 48, 1)[1] is False and box(12, 8, 48, 1)[0][2] > 1
+    assert box(6, 4, 48, 1)[1] is False
+    # VAE 384x256: a 128x1 row has as few tiles as a 16x8 box; 3x3 convolutions prefer the halo-compatible one
+    assert box(384, 256, 16, 0)[0] == (128, 1, 1)
+    assert box(384, 256, 16, 1) == ((16, 8, 1), True)
+    # a linear layer (h = n_img = 1) keeps the 128-row strip
+    assert box(73728, 1, 1, 0) == ((128, 1, 1), False)
+    # the tile count never grows because of the halo preference
+    for w, h, n in [(48, 32, 3), (20, 12, 2), (7, 5, 48), (40, 24, 2), (96, 64, 16)]:
+        (a, b, c), _ = box(w, h, n, 0)
+        (d, e, g), _ = box(w, h, n, 1)
+        tiles = lambda bw, bh, bn: -(-w // bw) * -(-h // bh) * -(-n // bn)
+        assert tiles(d, e, g) == tiles(a, b, c)
