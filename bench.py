@@ -1,19 +1,24 @@
 #!/usr/bin/env python
-"""bench.py — edited frames/sec @ 16 frames, 256x384, DDIM-50 (BASELINE.json metric) on N x B200.
+"""bench.py — edited frames/sec on N x B200 (BASELINE.json metric), default = configs[1]: 16 frames, 256x384, DDIM-50.
 
-One "step" = one complete edit of ONE 16-frame clip per GPU: 50 DDIM steps (each = one 3-branch-CFG UNet3D forward on
-[3,8,16,32,48] + fused CFG/DDIM update) followed by the KL-VAE decode of the 16 latents to 256x384 frames. With N GPUs
-every rank edits its own clip (weak scaling, clip-parallel) and the decoded frames are all-gathered once
-per step (NCCL). Synthetic N(0,1) latents / context, seeded random weights of the real architecture (no checkpoints
-exist offline).
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|flow|long|c1]
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+One "step" = one complete edit of ONE clip (or one chain of clips) per GPU; with N GPUs every rank edits its own
+(weak scaling, clip-parallel) and the decoded frames are all-gathered once per step (NCCL).
+  c2   configs[1]: 16-frame 256x384 clip, 50 DDIM steps (each = one CUDA graph: 3-branch-CFG UNet3D forward on
+       [3,8,16,32,48] + fused CFG/DDIM update), then the KL-VAE decode of the 16 latents.   (the default / headline)
+  flow configs[2]: a chained clip with --with_optical_flow: RAFT flows (12 query x 4 reference frames at 256x384),
+       50 DDIM steps with the warp-based noise correction on the first 25 (noise_correct_step 0.5), decode.
+  long configs[4]: 64-frame 384x576 video as the reference chains it (insv2v_run_loveu_tgve.py:123-161): one 16-frame
+       clip + 4 clips of 4 reference + 12 new frames, DDIM-100 each, UNet input [3,8,16,48,72], decode of 64 frames.
+  c1   configs[0]: 8-frame 256x256 clip, DDIM-20 (the CPU-runnable parity case).
+Synthetic N(0,1) latents / context, seeded random weights of the real architecture (no checkpoints exist offline).
 
 `value`  : frames/s with all inputs already resident in HBM.
 `e2e`    : same metric through the public API with HOST (pinned) inputs; H2D of latents/condition/context and D2H of the
            decoded frames inside the timed region.
-`roofline`: the dominant kernel (tcgen05 implicit-GEMM conv/linear, ivv_gemm) at its heaviest shape in this workload,
-           timed alone with CUDA events; algorithmic FLOPs / time vs the measured bf16 burst peak (MEASURED_PEAKS.json).
+`roofline`: the dominant kernel (tcgen05 implicit-GEMM conv, ivv_gemm) at its heaviest shape in this workload, timed
+           alone with CUDA events; `roofline.family` = time-weighted fractions per kernel family over one forward.
 `cpu_baseline` / `--impl reference`: the oracle (CPU restatement of the reference's PyTorch path, pinned to it by
            oracle/pin_against_reference.py) on the host cores, on a bounded sample, extrapolated to the same workload.
 """
@@ -30,11 +35,29 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FRAMES, LAT_H, LAT_W, DDIM_STEPS = 16, 32, 48, 50
 TEXT_CFG, IMG_CFG = 7.5, 1.5
-WORKLOAD = "configs[1]: 16-frame 256x384 clip, text-cfg 7.5 / video-cfg 1.5, DDIM-50, UNet3D [3,8,16,32,48] + VAE decode"
-# algorithmic FLOPs: UNet forward B=3 18.596 TF, VAE decode 0.935 TF per frame
-CLIP_TFLOP = DDIM_STEPS * 18.596 + FRAMES * 0.935
+FRAMES, LAT_H, LAT_W, DDIM_STEPS = 16, 32, 48, 50  # configs[1] shape (used by tools/)
+# algorithmic FLOPs: UNet forward B=3 on 16 frames: 18.596 TF at 32x48 latents, 6.126 TF for 8 frames at
+# 32x32, 43.99 TF at 48x72 (= (176.69 - 0.73) / 4: the 64-frame figure less its extra temporal-attention work);
+# VAE decode per frame 0.622 / 0.935 / 2.117 TF at 256x256 / 256x384 / 384x576; RAFT 0.55 TF per 4-pair call.
+WORKLOADS = {
+    "c2": dict(name="configs[1]: 16-frame 256x384 clip, text-cfg 7.5 / video-cfg 1.5, DDIM-50, UNet3D [3,8,16,32,48] "
+                    "+ VAE decode", frames=16, h=32, w=48, ddim=50, clips=1, unet_tf=18.596, vae_tf=0.935, out_frames=16),
+    "flow": dict(name="configs[2]: chained 16-frame 256x384 clip with optical-flow motion compensation (RAFT 12x4 pairs "
+                      "+ warp correction on steps 0-24), DDIM-50, + VAE decode", frames=16, h=32, w=48, ddim=50, clips=1,
+                 unet_tf=18.596, vae_tf=0.935, out_frames=16, raft_tf=12 * 0.55),
+    "long": dict(name="configs[4]: 64-frame 384x576 video as 16 + 4x(4 ref + 12 new) chained clips, DDIM-100, UNet3D "
+                      "[3,8,16,48,72] + VAE decode of 64 frames", frames=16, h=48, w=72, ddim=100, clips=5,
+                 unet_tf=43.99, vae_tf=2.117, out_frames=64),
+    "c1": dict(name="configs[0]: 8-frame 256x256 clip, DDIM-20, UNet3D [3,8,8,32,32] + VAE decode", frames=8, h=32, w=32,
+               ddim=20, clips=1, unet_tf=6.126, vae_tf=0.622, out_frames=8),
+}
+METRIC = {"c2": "edited frames/sec @16f 256x384 DDIM-50", "flow": "edited frames/sec @16f 256x384 DDIM-50 with optical flow",
+          "long": "edited frames/sec @64f 384x576 DDIM-100", "c1": "edited frames/sec @8f 256x256 DDIM-20"}
+
+
+def step_tflop(wl, ddim):
+    return wl["clips"] * ddim * wl["unet_tf"] + wl["out_frames"] * wl["vae_tf"] + wl.get("raft_tf", 0.0)
 
 
 def peaks():
@@ -94,25 +117,35 @@ def full_schema(name):
 
 def build_models(device):
     """Real architecture (configs/instruct_v2v_inference.yaml), seeded random weights."""
-    from oracle.insv2v_oracle import UNET_CONFIG_FULL, VAE_CONFIG_FULL  # config constants only
+    from insv2v_b200.configs import UNET_PARAMS, VAE_PARAMS
     from insv2v_b200.unet import UNet3DConditionModel
     from insv2v_b200.vae import AutoencoderKL
     torch.manual_seed(0)
-    unet = UNet3DConditionModel(**UNET_CONFIG_FULL)
+    unet = UNet3DConditionModel(**UNET_PARAMS)
     g = torch.Generator().manual_seed(1)
     with torch.no_grad():  # re-randomise the zero-initialised motion proj_out so the temporal path carries signal
         for n, p in unet.named_parameters():
             if "temporal_transformer.proj_out" in n:
                 p.copy_(torch.randn(p.shape, generator=g) * (0.02 if p.dim() > 1 else 0.01))
-    vae = AutoencoderKL(**VAE_CONFIG_FULL, lossconfig=None)
+    vae = AutoencoderKL(**VAE_PARAMS)
     return unet.to(device).eval(), vae.to(device).eval()
 
 
-def synth_inputs(seed, device=None, pinned=False):
+def synth_inputs(wl, seed, device=None, pinned=False, cfg="c2"):
     g = torch.Generator().manual_seed(seed)
-    d = dict(latent=torch.randn(1, FRAMES, 4, LAT_H, LAT_W, generator=g),
-             cond=torch.randn(1, FRAMES, 4, LAT_H, LAT_W, generator=g),
+    f, h, w = wl["frames"], wl["h"], wl["w"]
+    n_clip_frames = f if wl["clips"] == 1 else f + (wl["clips"] - 1) * 12
+    d = dict(latent=torch.randn(1, n_clip_frames, 4, h, w, generator=g),
+             cond=torch.randn(1, n_clip_frames, 4, h, w, generator=g),
              tc=torch.randn(1, 77, 768, generator=g), tu=torch.randn(1, 77, 768, generator=g))
+    if cfg == "flow":
+        d["latent_ref"] = torch.randn(1, 4, 4, h, w, generator=g)
+        # frames in [0, 1] for RAFT: a smooth pattern translated over time so that the flows are non-trivial
+        yy, xx = torch.meshgrid(torch.arange(8 * h, dtype=torch.float32), torch.arange(8 * w, dtype=torch.float32),
+                                indexing="ij")
+        fr = [0.5 + 0.25 * torch.sin(0.05 * (xx + 3 * i)) * torch.cos(0.04 * (yy - 2 * i)) + 0.05 *
+              torch.rand(3, 8 * h, 8 * w, generator=g) for i in range(16)]
+        d["frames"] = torch.stack(fr).unsqueeze(0).clamp(0, 1)  # [1, 16, 3, H, W]
     if pinned:
         d = {k: v.pin_memory() for k, v in d.items()}
     if device is not None:
@@ -120,15 +153,48 @@ def synth_inputs(seed, device=None, pinned=False):
     return d
 
 
-def top_gemm_roofline(pk):
-    """Time the heaviest single ivv_gemm shape of the workload alone: 3x3 conv 320->320 on 48 frames of 32x48
-    (ResnetBlock3D conv1/conv2 at level 0: 12 launches per UNet forward, 0.34 TFLOP... the largest FLOP share of any
-    one shape). CUDA events on the launching stream, L2 flushed by rotating over inputs > L2."""
+def make_step(cfg, wl, pipe):
+    """Returns edit(inputs dict on the device) -> decoded frames [1, out_frames, 3, H, W]."""
+    kw = dict(text_cfg=TEXT_CFG, img_cfg=IMG_CFG)
+    if cfg in ("c2", "c1"):
+        return lambda d: pipe.edit_clip(d["latent"], d["tc"], d["tu"], d["cond"], **kw)
+    if cfg == "flow":
+        def edit_flow(d):
+            # second_clip_forward of InferenceIP2PVideoOpticalFlow (inference.py:313-398): RAFT flows first
+            lat = pipe.denoise(d["latent"], d["tc"], d["tu"], d["cond"], latent_ref=d["latent_ref"],
+                               noise_correct_step=0.5, ref_images=d["frames"][:, :4], query_images=d["frames"][:, 4:],
+                               **kw)
+            return pipe.decode(lat)
+        return edit_flow
+
+    def edit_long(d):
+        # insv2v_run_loveu_tgve.py:123-161: first clip, then clips of 4 reference + 12 new frames, mean correction
+        f = wl["frames"]
+        lat_all, cond_all = d["latent"], d["cond"]
+        pred = pipe.denoise(lat_all[:, :f], d["tc"], d["tu"], cond_all[:, :f], **kw)
+        outs = [pred]
+        init = lat_all[:, :f]
+        for k in range(1, wl["clips"]):
+            lo = f + (k - 1) * 12
+            init = torch.cat([init[:, -4:], lat_all[:, lo:lo + 12]], dim=1)
+            cond = cond_all[:, lo - 4:lo + 12]
+            pred = pipe.denoise(init, d["tc"], d["tu"], cond, latent_ref=pred[:, -4:], noise_correct_step=0.5, **kw)
+            outs.append(pred[:, 4:])
+        lat = torch.cat(outs, dim=1)
+        return torch.cat([pipe.decode(lat[:, i:i + 16]) for i in range(0, lat.shape[1], 16)], dim=1)
+    return edit_long
+
+
+def top_gemm_roofline(pk, wl):
+    """Time the heaviest single ivv_gemm shape of the workload alone: 3x3 conv 320->320 (+bias) on 3*F frames at the
+    latent resolution (ResnetBlock3D conv1/conv2 at level 0: the largest FLOP share of any one shape). CUDA events on
+    the launching stream, L2 flushed by rotating over buffers > L2. tools/ncu_targets.py launches the same call for
+    the ncu --set full capture that `traffic` comes from."""
     from insv2v_b200 import ops
     dev = torch.device("cuda")
-    n, h, w, ci, co = 3 * FRAMES, LAT_H, LAT_W, 320, 320
+    n, h, w, ci, co = 3 * wl["frames"], wl["h"], wl["w"], 320, 320
     flops = 2.0 * n * h * w * ci * co * 9
-    nbuf = 6  # 6 x 47 MB activations + outputs > 126 MB L2
+    nbuf = 6  # 6 x (47 MB activations + 47 MB outputs) > 126 MB L2
     xs = [torch.randn(n * h * w, ci, device=dev).half() for _ in range(nbuf)]
     wt = ops.pack_conv3x3(torch.randn(co, ci, 3, 3, device=dev) * 0.02)
     b = torch.zeros(co, device=dev).half()
@@ -145,29 +211,95 @@ def top_gemm_roofline(pk):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     achieved = flops / (ms * 1e-3) / 1e12
-    traffic = None
-    tk = os.path.join(ROOT, "profiles", "r01_top_kernel.json")
-    if os.path.exists(tk):  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
-        j = json.load(open(tk))
-        traffic = j["dram_bytes_read"] + j["dram_bytes_write"]
-    return {"bound": "tensor", "kernel": "gemm_tc_persistent_kernel<160,4,32,...,HALO> conv3x3 320->320 on [48,32,48] frames",
-            "achieved": achieved,
-            "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"], "traffic": traffic,
-            "peak_source": pk["src"] + ", burst (kernel timed alone)", "ms_per_launch": ms,
-            "flops_per_launch": flops}
+    traffic, tk_src = None, None
+    for name in ("r02_top_kernel.json", "r01_top_kernel.json"):
+        tk = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tk):  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture
+            j = json.load(open(tk))
+            traffic, tk_src = j["dram_bytes_read"] + j["dram_bytes_write"], f"profiles/{name}"
+            break
+    return {"bound": "tensor", "kernel": f"gemm_tc_persistent_kernel<160,4,32,...,HALO> conv3x3 320->320 +bias on "
+                                         f"[{n},{h},{w}] frames",
+            "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"],
+            "traffic": traffic, "traffic_source": tk_src,
+            "peak_source": pk["src"] + ", burst (kernel timed alone)", "ms_per_launch": ms, "flops_per_launch": flops,
+            "algorithmic_bytes_per_launch": 2.0 * (n * h * w * (ci + co) + 9 * ci * co)}
 
 
-def cpu_baseline(threads, unet_frames=2, label="port"):
-    """Oracle on the host cores: one UNet forward at [3,8,unet_frames,32,48] (cost is linear in frames) + one
-    256x384 frame decode, extrapolated to 50 forwards of 16 frames + 16 decodes."""
+def family_roofline(unet, wl, pk):
+    """Time-weighted roofline per kernel family over ONE eager UNet3D forward at the workload's shape: CUDA events
+    around every C-ABI call (insv2v_b200.ops.Prof), algorithmic FLOPs / bytes summed per family and divided by the
+    family's summed device time. This is the figure that describes where a step's time goes; `roofline.achieved`
+    above describes the single best-fed kernel."""
+    from insv2v_b200 import ops
+    dev = torch.device("cuda")
+    x = torch.randn(3, 8, wl["frames"], wl["h"], wl["w"], device=dev)
+    ctx = torch.randn(3, 77, 768, device=dev)
+    t = torch.full((3,), 981.0, device=dev)
+    was = unet.use_cuda_graph
+    unet.use_cuda_graph = False
+    try:
+        unet(x, t, encoder_hidden_states=ctx)
+        torch.cuda.synchronize()
+        ops.Prof.enabled = True
+        unet(x, t, encoder_hidden_states=ctx)
+        agg = ops.Prof.report()
+    finally:
+        ops.Prof.enabled = False
+        unet.use_cuda_graph = was
+    fam = {}
+    for key, (n, ms, fl, nb) in agg.items():
+        name = key[0]
+        if name == "gemm":
+            name = "conv3x3" if key[2] >= 9 * 320 and key[2] % 9 == 0 and key[2] // 9 in (320, 640, 960, 1280, 1920,
+                                                                                             2560) else \
+                ("geglu_gemm" if key[4] == "geglu" else "linear")
+        a = fam.setdefault(name, [0, 0.0, 0.0, 0.0])
+        a[0] += n
+        a[1] += ms
+        a[2] += fl
+        a[3] += nb
+    out = {}
+    for name, (n, ms, fl, nb) in sorted(fam.items(), key=lambda kv: -kv[1][1]):
+        tfs, gbs = fl / ms / 1e9, nb / ms / 1e6
+        t_floor = max(fl / (pk["tf_sustained"] * 1e12), nb / (pk["hbm"] * 1e9)) * 1e3
+        out[name] = {"calls": n, "ms": round(ms, 3), "tflops": round(tfs, 1), "gbs": round(gbs, 0),
+                     "bound": "tensor" if fl / (pk["tf_sustained"] * 1e12) >= nb / (pk["hbm"] * 1e9) else "hbm",
+                     "frac_of_floor": round(t_floor / ms, 3)}
+    tot_ms = sum(v[1] for v in fam.values())
+    gem = [v for k, v in fam.items() if k in ("linear", "conv3x3", "geglu_gemm")]
+    gem_ms, gem_fl = sum(v[1] for v in gem), sum(v[2] for v in gem)
+    return {"per_family": out, "sum_ms": round(tot_ms, 3),
+            "gemm_family": {"tflop": round(gem_fl / 1e12, 3), "ms": round(gem_ms, 3),
+                            "achieved_tflops": round(gem_fl / gem_ms / 1e9, 1), "peak": pk["tf_sustained"],
+                            "frac": round(gem_fl / gem_ms / 1e9 / pk["tf_sustained"], 3)},
+            "method": "one eager forward, CUDA events around every call (warm L2, back to back); peaks sustained"}
+
+
+def attn_tensor_pipe():
+    """The metric's 'attn tensor-pipe %' per head dim: ncu sm__pipe_tensor_cycles_active of the attention kernels,
+    from the committed capture (a number measured under a profiler cannot be measured inside bench.py)."""
+    for name in ("r02_attn_tensor_pipe.json", "r01_attn_tensor_pipe.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            j = json.load(open(p))
+            j["source"] = f"profiles/{name}"
+            return j
+    return None
+
+
+def cpu_baseline(wl, threads, unet_frames=2, label="port"):
+    """Oracle on the host cores: one UNet forward at [3,8,unet_frames,h,w] + one frame decode, extrapolated to the
+    workload (DDIM steps x F/unet_frames forwards + F decodes). Assumes the forward's cost is linear in the number of
+    frames: every op is per frame except temporal attention, which is 0.15 % of the FLOPs."""
     from oracle import insv2v_oracle as O
     torch.set_num_threads(threads)
     sd = O.seeded_state_dict(full_schema("unet_full"), seed=0)
     vsd = O.seeded_state_dict(full_schema("vae_full"), seed=1)
     g = torch.Generator().manual_seed(0)
-    x = torch.randn(3, 8, unet_frames, LAT_H, LAT_W, generator=g)
+    x = torch.randn(3, 8, unet_frames, wl["h"], wl["w"], generator=g)
     ctx = torch.randn(3, 77, 768, generator=g)
-    z = torch.randn(1, 4, LAT_H, LAT_W, generator=g)
+    z = torch.randn(1, 4, wl["h"], wl["w"], generator=g)
     with torch.no_grad():
         t0 = time.perf_counter()
         O.unet3d_forward(sd, O.UNET_CONFIG_FULL, x, torch.tensor([981] * 3), ctx)
@@ -175,14 +307,18 @@ def cpu_baseline(threads, unet_frames=2, label="port"):
         t0 = time.perf_counter()
         O.vae_decode(vsd, O.VAE_CONFIG_FULL, z)
         t_dec = time.perf_counter() - t0
-    t_clip = DDIM_STEPS * t_unet * (FRAMES / unet_frames) + FRAMES * t_dec
-    return {"value": FRAMES / t_clip, "unit": "frames/s", "cores": threads, "kind": label,
-            "sample": f"1 UNet3D forward [3,8,{unet_frames},32,48] ({t_unet:.1f}s) x{FRAMES // unet_frames} per DDIM "
-                      f"step x{DDIM_STEPS} + 1 VAE frame decode 256x384 ({t_dec:.1f}s) x{FRAMES}; fp32, extrapolated",
-            "seconds_per_clip_extrapolated": t_clip}
+    t_step = wl["clips"] * wl["ddim"] * t_unet * (wl["frames"] / unet_frames) + wl["out_frames"] * t_dec
+    return {"value": wl["out_frames"] / t_step, "unit": "frames/s", "cores": threads, "kind": label,
+            "sample": f"1 UNet3D forward [3,8,{unet_frames},{wl['h']},{wl['w']}] ({t_unet:.1f}s) x"
+                      f"{wl['frames'] // unet_frames} per DDIM step x{wl['ddim']} x{wl['clips']} clip(s) + 1 VAE frame "
+                      f"decode ({t_dec:.1f}s) x{wl['out_frames']}; fp32, extrapolated",
+            "assumption": "forward cost linear in frames (temporal attention, the only cross-frame op, is 0.15 % of "
+                          "the FLOPs); a true 16-frame forward measured 56 s on 8 cores = 8 x 7.0 s "
+                          "(oracle/pin_full_size.py log)",
+            "seconds_per_step_extrapolated": t_step}
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, wl):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
@@ -190,15 +326,15 @@ def run_reference(args, rank):
     base = None
     uf = 2 if args.warmup + args.steps <= 8 else 1  # keep the whole run within a few minutes
     for i in range(args.warmup + args.steps):
-        base = cpu_baseline(threads, unet_frames=uf)
+        base = cpu_baseline(wl, threads, unet_frames=uf)
         if i >= args.warmup:
             vals.append(base["value"])
     v = sum(vals) / len(vals)
     base["value"] = v
-    line = {"impl": "reference", "metric": "edited frames/sec @16f 256x384 DDIM-50", "value": v, "unit": "frames/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * FRAMES / v,
+    line = {"impl": "reference", "metric": METRIC[args.config], "value": v, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wl["out_frames"] / v,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD}, "cpu_baseline": base,
+            "config": {"workload": wl["name"]}, "cpu_baseline": base,
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -209,15 +345,19 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ddim-steps", type=int, default=DDIM_STEPS, help=argparse.SUPPRESS)
+    ap.add_argument("--no-family", action="store_true")
+    ap.add_argument("--ddim-steps", type=int, default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    wl = WORKLOADS[args.config]
+    ddim = args.ddim_steps or wl["ddim"]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        return run_reference(args, rank)
+        return run_reference(args, rank, wl)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU arm)")
 
@@ -231,21 +371,35 @@ def main():
     lib.load()
     pk = peaks()
     unet, vae = build_models(dev)
-    pipe = InsV2VPipeline(unet, vae, num_ddim_steps=args.ddim_steps)
-    kw = dict(text_cfg=TEXT_CFG, img_cfg=IMG_CFG)
+    flow_estimator = None
+    if args.config == "flow":
+        from insv2v_b200.raft import RAFTFlow
+        torch.manual_seed(2)
+        flow_estimator = RAFTFlow().to(dev)
+        with torch.no_grad():
+            for p in flow_estimator.parameters():
+                if p.dim() > 1:
+                    p.normal_(0, (p[0].numel()) ** -0.5)
+                elif p.numel() > 0:
+                    p.normal_(0, 0.05)
+            for n_, p in flow_estimator.named_parameters():
+                if n_.endswith(".1.weight"):  # norm scales
+                    p.add_(1.0)
+    pipe = InsV2VPipeline(unet, vae, num_ddim_steps=ddim, flow_estimator=flow_estimator)
+    edit = make_step(args.config, wl, pipe)
+    oh, ow = wl["h"] * 8, wl["w"] * 8
 
-    dev_in = synth_inputs(1234 + rank, device=dev)
-    host_in = synth_inputs(1234 + rank, pinned=True)
-    host_out = torch.empty(1, FRAMES, 3, LAT_H * 8, LAT_W * 8, dtype=torch.float16).pin_memory()
+    dev_in = synth_inputs(wl, 1234 + rank, device=dev, cfg=args.config)
+    host_in = synth_inputs(wl, 1234 + rank, pinned=True, cfg=args.config)
+    host_out = torch.empty(1, wl["out_frames"], 3, oh, ow, dtype=torch.float16).pin_memory()
 
     def step_resident():
-        frames = pipe.edit_clip(dev_in["latent"], dev_in["tc"], dev_in["tu"], dev_in["cond"], **kw)
-        local_frames = frames.to(torch.float16)
+        local_frames = edit(dev_in).to(torch.float16)
         return parallel.gather_frames(local_frames, world, rank, world) if world > 1 else local_frames
 
     def step_e2e():
         d = {k: v.to(dev, non_blocking=True) for k, v in host_in.items()}
-        frames = pipe.edit_clip(d["latent"], d["tc"], d["tu"], d["cond"], **kw).to(torch.float16)
+        frames = edit(d).to(torch.float16)
         if world > 1:
             frames = parallel.gather_frames(frames, world, rank, world)[rank:rank + 1]
         host_out.copy_(frames, non_blocking=True)
@@ -279,7 +433,7 @@ def main():
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
-    total_frames = world * FRAMES * args.steps
+    total_frames = world * wl["out_frames"] * args.steps
     value = total_frames / (ms * 1e-3)
     e2e_value = total_frames / (ms_e2e * 1e-3)
     h2d = sum(v.numel() * v.element_size() for v in host_in.values())
@@ -289,25 +443,31 @@ def main():
         dist.destroy_process_group()
     if rank != 0:
         return
-    roof = top_gemm_roofline(pk)
-    step_tf = CLIP_TFLOP * (args.ddim_steps / DDIM_STEPS) / (ms * 1e-3 / args.steps)
+    roof = top_gemm_roofline(pk, wl)
+    if not args.no_family:
+        roof["family"] = family_roofline(unet, wl, pk)
+    atp = attn_tensor_pipe()
+    if atp is not None:
+        roof["attn_tensor_pipe_pct"] = atp
+    tf_step = step_tflop(wl, ddim)
+    step_tf = tf_step / (ms * 1e-3 / args.steps)
     line = {
-        "metric": "edited frames/sec @16f 256x384 DDIM-50", "value": value, "unit": "frames/s", "n_gpus": world,
+        "metric": METRIC[args.config], "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f16 (fp32 accumulate)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "clips_per_gpu_per_step": 1, "ddim_steps": args.ddim_steps,
+        "config": {"workload": wl["name"], "clips_per_gpu_per_step": wl["clips"], "ddim_steps": ddim,
                    "l2": "per-step working set (2.6 GB fp16 weights + activations) >> 126 MB L2; no explicit flush",
-                   "cuda_graph": True},
+                   "cuda_graph": "one graph per denoising step (begin + UNet3D + CFG/scheduler update)"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
         "roofline": roof,
-        "step_tensor_roofline": {"algorithmic_tflop_per_clip": CLIP_TFLOP, "achieved_tflops": step_tf,
+        "step_tensor_roofline": {"algorithmic_tflop_per_step": tf_step, "achieved_tflops": step_tf,
                                  "peak": pk["tf_sustained"], "frac": step_tf / pk["tf_sustained"],
                                  "peak_source": pk["src"] + ", sustained (whole step)"},
         "clocks": clk.summary(),
     }
     if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(os.cpu_count() or 1)
+        line["cpu_baseline"] = cpu_baseline(wl, os.cpu_count() or 1)
     print(json.dumps(line))
 
 

@@ -21,7 +21,7 @@ extern "C" {
 
 typedef void* ivv_stream_t; /* cudaStream_t */
 
-#define IVV_ABI_VERSION 2
+#define IVV_ABI_VERSION 3
 
 int ivv_abi_version(void);
 const char* ivv_last_error(void);
@@ -143,6 +143,32 @@ int ivv_flow_noise_correction(const float* delta_ref, const float* flow_lat, flo
  * eps3: fp32 [3, n] (branches uncond | image | text+image); latent fp32 [n] updated in place.                   */
 int ivv_cfg_ddim_step(const float* eps3, float* latent, float* eps_out, int64_t n, float text_cfg, float img_cfg,
                       float alpha_prod_t, float alpha_prod_prev, ivv_stream_t stream);
+
+/* ---- K13b: a whole sampling step around the UNet, graph-capturable without per-step host arguments ------------------
+ * The reference's loops (pl_trainer/inference/inference.py:163-219, 221-289, 313-398) do, per step: assemble the
+ * 3-branch UNet input, call the UNet, CFG-combine (:198-203), optional rescale_noise_cfg (:13-24, 205-206), optional
+ * reference-frame noise correction (mean :262-277 / optical flow :367-386), scheduler.step (diffusers 0.21.4 DDIM
+ * eta=0 or DDPM fixed_small). Here the host folds each step's scheduler scalars into one row of `table`
+ * (IVV_SAMPLER_ROW floats: t, sqrt(a_t), sqrt(1-a_t), c_x0, c_xt, c_eps, sigma, correct?, text_cfg, img_cfg,
+ * guidance_rescale, noise_row: prev = c_x0*x0 + c_xt*x_t + c_eps*eps + sigma*noise[noise_row]) once per clip; the
+ * kernels read the row selected by state[0], which ivv_sampler_update advances, so begin -> UNet -> combine -> update
+ * captured once is every step.  state: int32[4], zeroed by the caller before the first step.
+ * lat2: fp32 [2][F][C][hw] ping-pong latent (step s reads half s&1, writes half (s+1)&1); cond, eps_cfg: [F][C][hw].  */
+#define IVV_SAMPLER_ROW 16
+/* x_frames fp16 [3*F*hw, c_pad] = [latent | 0 or cond] for the branches (uncond, image, text+image); t_out[0..2] = t   */
+int ivv_sampler_begin(const float* table, const int32_t* state, const float* lat2, const float* cond, void* x_frames,
+                      float* t_out, int64_t frames, int64_t c, int64_t hw, int64_t c_pad, ivv_stream_t stream);
+/* eps3: UNet output frames fp32 [3*F*hw, eps_ld]; partials: double [ivv_sampler_partials(F, hw)][4]                   */
+int64_t ivv_sampler_partials(int64_t frames, int64_t hw);
+int ivv_sampler_combine(const float* table, const int32_t* state, const float* eps3, int64_t eps_ld, float* eps_cfg,
+                        double* partials, int64_t frames, int64_t c, int64_t hw, ivv_stream_t stream);
+/* mode 0: plain step; 1: mean correction from latent_ref [R][C][hw]; 2: flow correction, flows_lat [Q][R][2][hw] at
+ * latent resolution (query frame R+q, q < Q). noise: fp32 [rows][F*C*hw] or NULL (DDPM variance noise, drawn by the
+ * caller); hist_lat / hist_pred: fp32 [n_steps][F*C*hw] or NULL (the reference's all_latent / all_pred lists).        */
+int ivv_sampler_update(const float* table, int32_t* state, float* lat2, const float* eps_cfg, const double* partials,
+                       int32_t mode, const float* latent_ref, const float* flows_lat, const float* noise,
+                       float* hist_lat, float* hist_pred, int64_t frames, int64_t c, int64_t r, int64_t q, int64_t h,
+                       int64_t w, ivv_stream_t stream);
 
 /* ---- RAFT optical flow -------------------------------------------------------------------
  * The reference's RAFTFlow (misc_utils/flow_utils.py:134-189) wraps torchvision.models.optical_flow.raft_large

@@ -226,7 +226,21 @@ def conv3x3_s2(x, wgt_im2col, n_img, h, w, bias=None, pad=1):
 _ws_cache = {}
 
 
+class WS:
+    """Norm-statistics workspace policy. Eager calls share one zero-initialised buffer per (device, stream). A CUDA
+    graph must own its workspace (two graphs replayed on different streams would otherwise race on the ticket
+    counters): graph owners measure `high_water` over an eager warm-up pass, allocate their own zero-filled buffer
+    OUTSIDE capture and install it as `override` while capturing."""
+    override = None
+    high_water = 0
+
+
 def _gn_ws(nbytes, device):
+    WS.high_water = max(WS.high_water, nbytes)
+    if WS.override is not None:
+        if WS.override.numel() < nbytes or WS.override.device != device:
+            raise RuntimeError(f"graph-owned norm workspace too small ({WS.override.numel()} < {nbytes} bytes)")
+        return WS.override
     key = (device, torch.cuda.current_stream().cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
@@ -465,6 +479,9 @@ def flow_noise_correction_(eps, delta_ref, flow_lat):
     _chk32(eps, "eps"), _chk32(delta_ref, "delta_ref"), _chk32(flow_lat, "flow_lat")
     q, c, h, w = eps.shape
     r = delta_ref.shape[0]
+    if tuple(delta_ref.shape) != (r, c, h, w) or tuple(flow_lat.shape) != (q, r, 2, h, w):
+        raise ValueError(f"flow_noise_correction_: eps {tuple(eps.shape)} needs delta_ref [R,{c},{h},{w}] and flows "
+                         f"[{q},R,2,{h},{w}]; got {tuple(delta_ref.shape)} and {tuple(flow_lat.shape)}")
     _lib.check(_lib.load().ivv_flow_noise_correction(_p(delta_ref), _p(flow_lat), _p(eps), q, r, c, h, w, _s()),
                "ivv_flow_noise_correction")
     _count()
@@ -478,3 +495,52 @@ def cfg_ddim_step_(eps3, latent, text_cfg, img_cfg, alpha_t, alpha_prev, eps_out
                                              float(alpha_t), float(alpha_prev), _s()), "ivv_cfg_ddim_step")
     _count()
     return latent
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# fused sampling step (csrc/sampler.cu): begin -> UNet -> combine -> update, all parameters read from device memory
+# ----------------------------------------------------------------------------------------------------------------
+SAMPLER_ROW = 16  # IVV_SAMPLER_ROW
+
+
+def sampler_partials(frames, hw):
+    return int(_lib.load().ivv_sampler_partials(frames, hw))
+
+
+def sampler_begin(table, state, lat2, cond, x_frames, t_out, frames, c, hw, c_pad):
+    _chk32(table, "table"), _chk32(lat2, "lat2"), _chk32(cond, "cond"), _chk32(t_out, "t_out"), _chk16(x_frames, "x")
+    if x_frames.shape != (3 * frames * hw, c_pad) or lat2.numel() != 2 * frames * c * hw or cond.numel() != frames * c * hw:
+        raise ValueError("sampler_begin: buffer shapes do not match (frames, c, hw, c_pad)")
+    _lib.check(_lib.load().ivv_sampler_begin(_p(table), _p(state), _p(lat2), _p(cond), _p(x_frames), _p(t_out), frames,
+                                             c, hw, c_pad, _s()), "ivv_sampler_begin")
+    _count()
+
+
+def sampler_combine(table, state, eps3, eps_cfg, partials, frames, c, hw):
+    _chk32(eps3, "eps3"), _chk32(eps_cfg, "eps_cfg")
+    if eps3.shape[0] != 3 * frames * hw or eps3.shape[1] < c or eps_cfg.numel() != frames * c * hw:
+        raise ValueError("sampler_combine: buffer shapes do not match (frames, c, hw)")
+    if partials.dtype != torch.float64 or partials.numel() < 4 * sampler_partials(frames, hw):
+        raise ValueError("sampler_combine: partials must be float64 [ivv_sampler_partials, 4]")
+    _lib.check(_lib.load().ivv_sampler_combine(_p(table), _p(state), _p(eps3), eps3.stride(0), _p(eps_cfg), _p(partials),
+                                               frames, c, hw, _s()), "ivv_sampler_combine")
+    _count()
+
+
+def sampler_update(table, state, lat2, eps_cfg, partials, mode, latent_ref, flows_lat, noise, hist_lat, hist_pred,
+                   frames, c, r, q, h, w):
+    n = frames * c * h * w
+    for t, name, numel in ((latent_ref, "latent_ref", r * c * h * w), (flows_lat, "flows_lat", q * r * 2 * h * w)):
+        if t is not None:
+            _chk32(t, name)
+            if t.numel() != numel:
+                raise ValueError(f"sampler_update: {name} has {t.numel()} elements, expected {numel}")
+    for t, name in ((noise, "noise"), (hist_lat, "hist_lat"), (hist_pred, "hist_pred")):
+        if t is not None:
+            _chk32(t, name)
+            if t.numel() % n != 0:
+                raise ValueError(f"sampler_update: {name} must be [rows, {n}]")
+    _lib.check(_lib.load().ivv_sampler_update(_p(table), _p(state), _p(lat2), _p(eps_cfg), _p(partials), mode,
+                                              _p(latent_ref), _p(flows_lat), _p(noise), _p(hist_lat), _p(hist_pred),
+                                              frames, c, r, q, h, w, _s()), "ivv_sampler_update")
+    _count()

@@ -49,11 +49,12 @@ def gather_frames(local_frames, n_clips, rank, world):
 
 def run_clips(edit_fn, clip_inputs, rank, world):
     """edit_fn(clip_input) -> [F, 3, H, W]; clip_inputs: list of per-clip inputs (same on every rank).
-    Each rank edits its own clips; all ranks return all decoded clips."""
+    Each rank edits its own clips; all ranks return all decoded clips. Needs at least one clip per rank: the check is
+    the same deterministic condition on EVERY rank and runs before any work, so a short job fails everywhere instead
+    of leaving the ranks that own clips waiting in the all-gather."""
+    if len(clip_inputs) < world:
+        raise ValueError(f"run_clips: {len(clip_inputs)} clips for {world} ranks; every rank needs at least one clip "
+                         "(launch with fewer ranks, or batch more clips)")
     mine = clips_for_rank(len(clip_inputs), rank, world)
-    outs = [edit_fn(clip_inputs[i]) for i in mine]
-    if outs:
-        local = torch.stack(outs, dim=0)
-    else:
-        raise ValueError("a rank without clips cannot infer the frame shape; use n_clips >= world")
+    local = torch.stack([edit_fn(clip_inputs[i]) for i in mine], dim=0)
     return gather_frames(local, len(clip_inputs), rank, world)

@@ -314,14 +314,21 @@ class _Graph:
         self.a, self.b = img1.clone(), img2.clone()
         stream = torch.cuda.Stream(device=img1.device)
         stream.wait_stream(torch.cuda.current_stream())
+        ops.WS.high_water = 0
         with torch.cuda.stream(stream):
             eng.run(self.a, self.b, size)  # warm-up: lazy kernel attribute setup happens outside the capture
         torch.cuda.current_stream().wait_stream(stream)
         torch.cuda.synchronize()
+        # graph-owned norm-statistics workspace (ticket counters), zero-filled outside capture (see ops.WS)
+        self.ws = torch.zeros(max(ops.WS.high_water, 1 << 16), dtype=torch.uint8, device=img1.device)
         n0 = _lib.LAUNCH_COUNT
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out = eng.run(self.a, self.b, size)
+        ops.WS.override = self.ws
+        try:
+            with torch.cuda.graph(self.graph):
+                self.out = eng.run(self.a, self.b, size)
+        finally:
+            ops.WS.override = None
         self.n_launches = _lib.LAUNCH_COUNT - n0
 
     def replay(self, img1, img2):

@@ -321,6 +321,7 @@ class UNet3DConditionModel(nn.Module):
 
         self._engine = None
         self.use_cuda_graph = True
+        self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module.invalidate())
 
     # ---- reference API surface -------------------------------------------------------------------------------
     @property
@@ -358,13 +359,19 @@ class UNet3DConditionModel(nn.Module):
         self._engine = None  # packed weights follow the parameters (device / dtype moves)
         return super()._apply(fn, recurse)
 
-    def load_state_dict(self, state_dict, strict=True, **kw):
-        self._engine = None
-        return super().load_state_dict(state_dict, strict=strict, **kw)
-
     def invalidate(self):
-        """Drop packed weights and captured graphs (call after mutating parameters in place)."""
+        """Drop packed weights and captured graphs. Called automatically: by the load-state-dict post hook (fires
+        also when a PARENT module loads a checkpoint, as insv2v_run_loveu_tgve.py:60-62 does through the Lightning
+        container) and by the weight stamp check in engine() (in-place edits, sub-module loads)."""
         self._engine = None
+
+    def engine(self, device):
+        """Packed weights + launch plan for `device`, rebuilt whenever the parameters changed since packing."""
+        stamp = weights_stamp(self)
+        if self._engine is None or self._engine.device != device or self._engine.stamp != stamp:
+            self._engine = _Engine(self, device)
+            self._engine.stamp = stamp
+        return self._engine
 
     # ---- forward ---------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -375,8 +382,7 @@ class UNet3DConditionModel(nn.Module):
         if not sample.is_cuda:
             raise RuntimeError("insv2v_b200.UNet3DConditionModel runs only on CUDA (sm_100a); there is no CPU path. "
                                "Use oracle/insv2v_oracle.py for a CPU evaluation.")
-        if self._engine is None or self._engine.device != sample.device:
-            self._engine = _Engine(self, sample.device)
+        eng = self.engine(sample.device)
         # timestep handling mirrors unet.py:343-356
         t = timestep
         if not torch.is_tensor(t):
@@ -386,7 +392,7 @@ class UNet3DConditionModel(nn.Module):
         t = t.to(device=sample.device, dtype=torch.float32).expand(sample.shape[0]).contiguous()
         # attention_mask is converted by the reference (unet.py:334-336) but never reaches the transformers
         # (unet_blocks.py:353 does not forward it): it has no effect there either.
-        out = self._engine.run(sample, t, encoder_hidden_states, int(video_start_index), self.use_cuda_graph)
+        out = eng.run(sample, t, encoder_hidden_states, int(video_start_index), self.use_cuda_graph)
         out = out.to(sample.dtype) if sample.dtype != out.dtype else out
         if not return_dict:
             return (out,)
@@ -396,6 +402,22 @@ class UNet3DConditionModel(nn.Module):
 # ------------------------------------------------------------------------------------------------------------------
 # execution plan
 # ------------------------------------------------------------------------------------------------------------------
+def weights_stamp(module):
+    """Cheap fingerprint of a module's parameters and buffers: every in-place write bumps a tensor's `_version`, every
+    re-allocation (`.to()`, `.data = ...`, load with assign=True) changes its `data_ptr`. Packed fp16 weights and
+    captured CUDA graphs are valid only for the stamp they were built from."""
+    v, a, n = 0, 0, 0
+    for t in module.parameters():
+        v += t._version
+        a ^= t.data_ptr()
+        n += 1
+    for t in module.buffers():
+        v += t._version
+        a ^= t.data_ptr()
+        n += 1
+    return (n, v, a)
+
+
 def _h(t, device):
     return t.detach().to(device=device, dtype=F16).contiguous()
 
@@ -611,17 +633,15 @@ class _Engine:
         return kvs
 
     # ---- one forward ---------------------------------------------------------------------------------------
-    def _forward_frames(self, sample, t, ctx, pe_start, ctx_kv=None):
-        b, cin, f, h, w = sample.shape
-        st = dict(b=b, f=f, n=b * f, h=h, w=w, pe_start=pe_start)
-        st["ctx_kv"] = self._context_kv(ctx) if ctx_kv is None else ctx_kv
-        st["ctx_len"] = ctx.shape[1]
+    def forward_body(self, x, t, b, f, h, w, pe_start, ctx_kv, ctx_len):
+        """x: input frames [b*f*h*w, cin_pad] fp16 (channels-last), t fp32 [b] on the device. Returns the UNet output
+        as frames [b*f*h*w, out_channels] fp32 and its (h, w)."""
+        st = dict(b=b, f=f, n=b * f, h=h, w=w, pe_start=pe_start, ctx_kv=ctx_kv, ctx_len=ctx_len)
         W = self.w
         # time embedding: sinusoid -> linear_1 -> SiLU -> linear_2 -> SiLU -> all time_emb_proj at once
         te = ops.timestep_embedding(t, W["te1"][0].shape[2], self.cfg["flip_sin_to_cos"], self.cfg["freq_shift"])
         te = ops.linear(ops.silu(ops.linear(te, W["te1"][0], bias=W["te1"][1])), W["te2"][0], bias=W["te2"][1])
         st["temb"] = ops.linear(ops.silu(te), self.temb_w, bias=self.temb_b)  # [b, sum(cout)]
-        x = ops.ncfhw_to_frames(sample, self.cin_pad)
         x = ops.conv3x3(x, W["conv_in"][0], st["n"], h, w, bias=W["conv_in"][1])
         skips = [(x, h, w)]
         default_up = 2 ** self.num_upsamplers
@@ -654,17 +674,27 @@ class _Engine:
         g, be, eps, groups = W["norm_out"]
         x = ops.groupnorm(x, g, be, st["n"], st["h"] * st["w"], groups, f, eps, True)
         x = ops.conv3x3(x, W["conv_out"][0], st["n"], st["h"], st["w"], bias=W["conv_out"][1], out_f32=True)
-        return ops.frames_to_ncfhw(x, b, self.out_channels, f, st["h"], st["w"], torch.float32)
+        return x, st["h"], st["w"]
 
-    def run(self, sample, t, ctx, video_start_index, use_graph):
-        f = sample.shape[2]
+    def _forward_frames(self, sample, t, ctx, pe_start, ctx_kv=None):
+        b, cin, f, h, w = sample.shape
+        ctx_kv = self._context_kv(ctx) if ctx_kv is None else ctx_kv
+        x = ops.ncfhw_to_frames(sample, self.cin_pad)
+        x, ho, wo = self.forward_body(x, t, b, f, h, w, pe_start, ctx_kv, ctx.shape[1])
+        return ops.frames_to_ncfhw(x, b, self.out_channels, f, ho, wo, torch.float32)
+
+    def pe_start_for(self, video_start_index, f):
+        """PositionalEncoding.forward, motion_module.py:236-240."""
         pe_start = video_start_index
         if self.pe_len is not None:
-            # PositionalEncoding.forward, motion_module.py:236-240
             if pe_start + f > self.pe_len:
                 pe_start = pe_start - self.pe_len
             if pe_start < 0:
                 raise ValueError(f"start_index must be non-negative, but got {pe_start}")
+        return pe_start
+
+    def run(self, sample, t, ctx, video_start_index, use_graph):
+        pe_start = self.pe_start_for(video_start_index, sample.shape[2])
         if ctx.shape[0] != sample.shape[0]:
             raise ValueError(f"encoder_hidden_states batch {ctx.shape[0]} != sample batch {sample.shape[0]}")
         if not use_graph:
@@ -691,16 +721,23 @@ class _Graph:
         self.ctx_ref, self.ctx_ver = None, -1  # the context object the static K/V were computed from
         stream = torch.cuda.Stream(device=sample.device)
         stream.wait_stream(torch.cuda.current_stream())
+        ops.WS.high_water = 0
         with torch.cuda.stream(stream):
             self.ctx_kv = eng._context_kv(self.c_in)
             eng._forward_frames(self.s_in, self.t_in, self.c_in, pe_start, self.ctx_kv)  # warm-up: lazy kernel setup
         torch.cuda.current_stream().wait_stream(stream)
         torch.cuda.synchronize()
+        # the graph owns its norm-statistics workspace (ticket counters): zero-filled here, outside capture
+        self.ws = torch.zeros(max(ops.WS.high_water, 1 << 16), dtype=torch.uint8, device=sample.device)
         from . import lib as _lib
         n0 = _lib.LAUNCH_COUNT
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out = eng._forward_frames(self.s_in, self.t_in, self.c_in, pe_start, self.ctx_kv)
+        ops.WS.override = self.ws
+        try:
+            with torch.cuda.graph(self.graph):
+                self.out = eng._forward_frames(self.s_in, self.t_in, self.c_in, pe_start, self.ctx_kv)
+        finally:
+            ops.WS.override = None
         self.n_launches = _lib.LAUNCH_COUNT - n0  # kernels inside the graph: counted again on every replay
         self._lib = _lib
 

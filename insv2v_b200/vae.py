@@ -9,7 +9,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .unet import _Holder, _h
+from .unet import _Holder, _h, weights_stamp
 
 F16 = torch.float16
 
@@ -135,6 +135,7 @@ class AutoencoderKL(nn.Module):
         self.post_quant_conv = nn.Conv2d(embed_dim, dd["z_channels"], 1)
         self.embed_dim = embed_dim
         self._packed = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible_keys: module.invalidate())
         if ckpt_path is not None:
             self.init_from_ckpt(ckpt_path, ignore_keys=list(ignore_keys))
 
@@ -149,9 +150,17 @@ class AutoencoderKL(nn.Module):
         self._packed = None
         return super()._apply(fn, recurse)
 
-    def load_state_dict(self, state_dict, strict=True, **kw):
+    def invalidate(self):
+        """Drop the packed weights (automatic: load-state-dict post hook + weight stamp, see unet.weights_stamp)."""
         self._packed = None
-        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def packed(self, dev):
+        stamp = weights_stamp(self)
+        P = self._packed
+        if P is None or P["device"] != dev or P["stamp"] != stamp:
+            P = self._pack(dev)
+            P["stamp"] = stamp
+        return P
 
     # ---- packing ---------------------------------------------------------------------------------------------
     def _pack(self, dev):
@@ -235,7 +244,7 @@ class AutoencoderKL(nn.Module):
         """z [n, z_channels, h, w] -> image [n, out_ch, 8h, 8w] (dtype follows z)."""
         if not z.is_cuda:
             raise RuntimeError("insv2v_b200.AutoencoderKL runs only on CUDA (sm_100a); there is no CPU path")
-        P = self._packed if self._packed is not None and self._packed["device"] == z.device else self._pack(z.device)
+        P = self.packed(z.device)
         n, zc, h, w = z.shape
         x = ops.ncfhw_to_frames(z.reshape(n, zc, 1, h, w), 8)
         x = ops.linear(x, P["pq"][0], bias=P["pq"][1])
@@ -261,7 +270,7 @@ class AutoencoderKL(nn.Module):
         """Encoder + quant_conv: image [n, 3, H, W] -> moments [n, 2*embed_dim, H/8, W/8] (mean | logvar), fp32."""
         if not x.is_cuda:
             raise RuntimeError("insv2v_b200.AutoencoderKL runs only on CUDA (sm_100a); there is no CPU path")
-        P = self._packed if self._packed is not None and self._packed["device"] == x.device else self._pack(x.device)
+        P = self.packed(x.device)
         n, c, h, w = x.shape
         t = ops.ncfhw_to_frames(x.reshape(n, c, 1, h, w), 8)
         t = ops.conv3x3(t, P["e_in"][0], n, h, w, bias=P["e_in"][1])

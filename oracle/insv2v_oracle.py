@@ -87,7 +87,7 @@ def seeded_state_dict(schema, seed):
 def timestep_sinusoid(timesteps, dim, flip_sin_to_cos=True, freq_shift=0.0):
     """diffusers get_timestep_embedding (models/embeddings.py), called through Timesteps at unet.py:358."""
     half = dim // 2
-    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32) / (half - freq_shift)
+    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32, device=timesteps.device) / (half - freq_shift)
     emb = timesteps[:, None].float() * torch.exp(exponent)[None, :]
     emb = torch.cat([torch.sin(emb), torch.cos(emb)], dim=-1)
     if flip_sin_to_cos:
@@ -330,6 +330,35 @@ def decode_latent_to_image(sd, cfg, latents, scale_factor=0.18215):
     return torch.stack(frames, dim=1)
 
 
+def vae_encode_moments(sd, cfg, x):
+    """AutoencoderKL.encode up to the moments (autoencoder.py:89-91): Encoder.forward (vqvae/model.py:275-302; attn
+    lists are empty for attn_resolutions=()), Downsample with the asymmetric (0,1,0,1) zero pad (:67-71), quant_conv.
+    x [n, 3, H, W] -> moments [n, 2*embed_dim, H/8, W/8] (mean | logvar)."""
+    dd = cfg["ddconfig"]
+    nres = len(dd["ch_mult"])
+    h = _conv(sd, "encoder.conv_in", x, 1)
+    for lvl in range(nres):
+        for blk in range(dd["num_res_blocks"]):
+            h = vae_resnet(sd, f"encoder.down.{lvl}.block.{blk}", h)
+        if lvl != nres - 1:
+            h = F.conv2d(F.pad(h, (0, 1, 0, 1)), sd[f"encoder.down.{lvl}.downsample.conv.weight"],
+                         sd[f"encoder.down.{lvl}.downsample.conv.bias"], stride=2)
+    h = vae_resnet(sd, "encoder.mid.block_1", h)
+    h = vae_attn(sd, "encoder.mid.attn_1", h)
+    h = vae_resnet(sd, "encoder.mid.block_2", h)
+    h = _conv(sd, "encoder.conv_out", F.silu(_vae_norm(sd, "encoder.norm_out", h)), 1)
+    return _conv(sd, "quant_conv", h, 0)
+
+
+def vae_encode(sd, cfg, x, noise=None):
+    """AutoencoderKL.encode (autoencoder.py:89-95) = DiagonalGaussianDistribution(moments).sample() (:10-24): logvar
+    clamped to [-30, 20], mean + exp(0.5 logvar) * randn drawn on the CPU default generator and moved to the device."""
+    mean, logvar = torch.chunk(vae_encode_moments(sd, cfg, x), 2, dim=1)
+    std = torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0))
+    noise = torch.randn(mean.shape) if noise is None else noise
+    return mean + std * noise.to(mean.device)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # misc_utils/flow_utils.py
 # ------------------------------------------------------------------------------------------------------------------
@@ -341,7 +370,7 @@ def warp_image(image, flow, mode="bilinear"):
         flow = flow.unsqueeze(0)
     assert image.shape[0] == flow.shape[0] and image.shape[2:] == flow.shape[2:]
     n, _, h, w = image.shape
-    ys, xs = torch.meshgrid(torch.arange(h), torch.arange(w), indexing="ij")
+    ys, xs = torch.meshgrid(torch.arange(h, device=image.device), torch.arange(w, device=image.device), indexing="ij")
     grid = torch.stack([xs, ys], dim=-1).to(torch.float32)[None].repeat(n, 1, 1, 1)
     grid = grid + flow.permute(0, 2, 3, 1)
     gx = 2 * (grid[..., 0] / (w - 1) - 0.5)
@@ -374,6 +403,12 @@ def ddim_timesteps(num_steps, n_train=1000, steps_offset=1):
     return [int(i * ratio + steps_offset) for i in reversed(range(num_steps))]
 
 
+def ddpm_timesteps(num_steps, n_train=1000):
+    """DDPMScheduler.set_timesteps, timestep_spacing='leading' (no steps_offset): 950, 900 ... 0 for 20 steps."""
+    ratio = n_train // num_steps
+    return [int(i * ratio) for i in reversed(range(num_steps))]
+
+
 def ddim_step(ac, eps, t, x, num_steps, n_train=1000):
     """DDIMScheduler.step with eta=0, epsilon prediction, clip_sample=False, set_alpha_to_one=False."""
     prev_t = t - n_train // num_steps
@@ -383,26 +418,69 @@ def ddim_step(ac, eps, t, x, num_steps, n_train=1000):
     return a_prev ** 0.5 * x0 + (1 - a_prev) ** 0.5 * eps, x0
 
 
+def ddpm_coefficients(ac, t, num_steps, n_train=1000):
+    """The scalars of DDPMScheduler.step (diffusers 0.21.4, epsilon prediction, variance_type='fixed_small',
+    clip_sample=False): returns (sqrt(1-a_t), sqrt(a_t), x0 coefficient, sample coefficient, sigma). The posterior
+    mean is c0*x0 + cs*x_t (DDPM eq. 7) and sigma^2 = clamp((1-a_prev)/(1-a_t) * beta_t, 1e-20) for t > 0, else 0."""
+    prev_t = t - n_train // num_steps
+    a_t = ac[t]
+    a_prev = ac[prev_t] if prev_t >= 0 else torch.tensor(1.0)
+    cur_alpha = a_t / a_prev
+    cur_beta = 1 - cur_alpha
+    c0 = (a_prev ** 0.5 * cur_beta) / (1 - a_t)
+    cs = cur_alpha ** 0.5 * (1 - a_prev) / (1 - a_t)
+    var = torch.clamp((1 - a_prev) / (1 - a_t) * cur_beta, min=1e-20)
+    sigma = var ** 0.5 if t > 0 else torch.tensor(0.0)
+    return (1 - a_t) ** 0.5, a_t ** 0.5, c0, cs, sigma
+
+
+def ddpm_step(ac, eps, t, x, num_steps, n_train=1000, generator=None):
+    """DDPMScheduler.step: the variance noise is torch.randn(eps.shape) on the (global, unless given) CPU generator."""
+    sb, sa, c0, cs, sigma = ddpm_coefficients(ac, t, num_steps, n_train)
+    x0 = (x - sb * eps) / sa
+    prev = c0 * x0 + cs * x
+    if t > 0:
+        prev = prev + sigma * torch.randn(eps.shape, generator=generator, dtype=eps.dtype).to(eps.device)
+    return prev, x0
+
+
 def cfg_combine(e1, e2, e3, text_cfg, img_cfg):
     """inference.py:198-203."""
     return e1 + img_cfg * (e2 - e1) + text_cfg * (e3 - e2)
 
 
+def rescale_noise_cfg(noise_cfg, noise_pred_text, guidance_rescale=0.0):
+    """inference.py:13-24: unbiased std over all but the batch dim; NOTE the reference passes noise_pred1 (the fully
+    unconditional branch) as `noise_pred_text` (:205-206), which is mirrored by the callers below."""
+    dims = list(range(1, noise_pred_text.ndim))
+    std_text = noise_pred_text.std(dim=dims, keepdim=True)
+    std_cfg = noise_cfg.std(dim=dims, keepdim=True)
+    rescaled = noise_cfg * (std_text / std_cfg)
+    return guidance_rescale * rescaled + (1 - guidance_rescale) * noise_cfg
+
+
 def sample_ip2p_video(unet_fn, latent, text_cond, text_uncond, img_cond, text_cfg=7.5, img_cfg=1.2, num_steps=20,
-                      latent_ref=None, noise_correct_step=1.0, flows=None):
+                      latent_ref=None, noise_correct_step=1.0, flows=None, scheduler="ddim", start_time=0,
+                      guidance_rescale=0.0, return_all=False, generator=None):
     """InferenceIP2PVideo.__call__ (inference.py:163-219), .second_clip_forward (:221-289) when latent_ref is given,
     and InferenceIP2PVideoOpticalFlow.second_clip_forward (:314-398) when flows [Q][R,2,H,W] are given too.
-    unet_fn(x [3, 8, f, h, w], t LongTensor[3], ctx [3, 77, c]) -> eps [3, 4, f, h, w]. DDIM scheduler."""
+    unet_fn(x [3, 8, f, h, w], t LongTensor[3], ctx [3, 77, c]) -> eps [3, 4, f, h, w]. scheduler 'ddim' | 'ddpm'
+    (inference.py:35-49). The loop index i restarts at 0 when start_time > 0 (enumerate over the sliced timesteps,
+    :181,240), so the noise-correction window counts from the first executed step, as in the reference."""
     ac = alphas_cumprod()
     latent = latent.clone()
-    for i, t in enumerate(ddim_timesteps(num_steps)):
+    steps = ddim_timesteps(num_steps) if scheduler == "ddim" else ddpm_timesteps(num_steps)
+    all_latent, all_pred = [], []
+    for i, t in enumerate(steps[start_time:]):
         l1 = torch.cat([latent, torch.zeros_like(img_cond)], dim=2)
         l2 = torch.cat([latent, img_cond], dim=2)
         x = torch.cat([l1, l2, l2.clone()], dim=0).permute(0, 2, 1, 3, 4)  # 'b f c h w -> b c f h w'
         ctx = torch.cat([text_uncond, text_uncond, text_cond], dim=0)
-        eps = unet_fn(x, torch.full((3,), t, dtype=torch.long), ctx).permute(0, 2, 1, 3, 4)
+        eps = unet_fn(x, torch.full((3,), t, dtype=torch.long, device=x.device), ctx).permute(0, 2, 1, 3, 4)
         e1, e2, e3 = eps.chunk(3, dim=0)
         eps = cfg_combine(e1, e2, e3, text_cfg, img_cfg)
+        if guidance_rescale > 0:
+            eps = rescale_noise_cfg(eps, e1, guidance_rescale)
         if latent_ref is not None and noise_correct_step * num_steps > i:
             r = latent_ref.shape[1]
             a_t = ac[t]
@@ -421,5 +499,12 @@ def sample_ip2p_video(unet_fn, latent, text_cond, text_uncond, img_cond, text_cf
                     corr = torch.where(msum > 0.5, warped[None].sum(dim=1, keepdim=True) / msum,
                                        torch.zeros_like(msum))
                     eps[:, q:q + 1] += torch.where(msum > 0.5, corr, torch.zeros_like(corr))
-        latent, _ = ddim_step(ac, eps, t, latent, num_steps)
+        if scheduler == "ddim":
+            latent, x0 = ddim_step(ac, eps, t, latent, num_steps)
+        else:
+            latent, x0 = ddpm_step(ac, eps, t, latent, num_steps, generator=generator)
+        all_latent.append(latent)
+        all_pred.append(x0)
+    if return_all:
+        return {"latent": latent, "all_latent": all_latent, "all_pred": all_pred}
     return latent

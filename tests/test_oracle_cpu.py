@@ -120,3 +120,57 @@ def test_raft_golden_is_the_oracles_output():
     with torch.no_grad():
         flow = R.raft_flow(sd, g["img1"].float() / 255, g["img2"].float() / 255)
     _close(flow, g["flow"], 1e-5)
+
+
+# ---- goldens minted at the benchmarked sizes / for the entry script's scheduler (oracle/pin_full_size.py) ----------
+@pytest.mark.parametrize("tag", ["tiny", "full"])
+def test_oracle_vae_encoder_matches_reference_golden(tag):
+    cfg = {"tiny": O.VAE_CONFIG_TINY, "full": O.VAE_CONFIG_FULL}[tag]
+    g = golden(f"vae_encoder_{tag}.pt")
+    sd = O.seeded_state_dict(schema(f"vae_encoder_{tag}"), seed=g["weight_seed"])
+    with torch.no_grad():
+        m = O.vae_encode_moments(sd, cfg, seeded(g["x_shape"], g["x_seed"]))
+    _close(m, g["moments"])
+    torch.manual_seed(3)
+    z = O.vae_encode(sd, cfg, seeded(g["x_shape"], g["x_seed"]))
+    torch.manual_seed(3)
+    mean, logvar = m.chunk(2, dim=1)
+    assert torch.allclose(z, mean + torch.exp(0.5 * logvar.clamp(-30, 20)) * torch.randn(mean.shape), atol=1e-6)
+
+
+def test_oracle_vae_full_config_matches_reference_golden():
+    g = golden("vae_full_decode.pt")
+    sd = O.seeded_state_dict(schema("vae_full"), seed=g["weight_seed"])
+    with torch.no_grad():
+        y = O.vae_decode(sd, O.VAE_CONFIG_FULL, seeded(g["z_shape"], g["z_seed"])[:1])
+    _close(y, g["out"][:1])
+
+
+def test_oracle_ddpm_rescale_start_time_match_reference_golden():
+    cfg = O.UNET_CONFIG_MICRO
+    g = golden("sampler_micro_ddpm.pt")
+    s = g["seeds"]
+    sd = O.seeded_state_dict(schema("unet_micro"), seed=g["weight_seed"])
+    cd = cfg["cross_attention_dim"]
+    lat, cond = seeded((1, 6, 4, 16, 16), s["lat"]), seeded((1, 6, 4, 16, 16), s["cond"])
+    tc, tu = seeded((1, 77, cd), s["tc"]), seeded((1, 77, cd), s["tu"])
+    lref = seeded((1, 2, 4, 16, 16), s["lref"])
+    flows = [seeded((2, 2, 128, 128), s["flow0"] + q, 6.0) for q in range(4)]
+    assert O.ddpm_timesteps(4) == g["ddpm_timesteps_4"] and O.ddpm_timesteps(20) == g["ddpm_timesteps_20"]
+
+    def run(**kw):
+        torch.manual_seed(g["noise_seed"])
+        with torch.no_grad():
+            return O.sample_ip2p_video(lambda x, t, c: O.unet3d_forward(sd, cfg, x, t, c), lat, tc, tu, cond,
+                                       g["text_cfg"], g["img_cfg"], g["steps"], return_all=True, **kw)
+    for name, kw in (("ddpm_first", dict(scheduler="ddpm")),
+                     ("ddpm_rescale_start1", dict(scheduler="ddpm", guidance_rescale=0.7, start_time=1)),
+                     ("ddpm_second_mean", dict(scheduler="ddpm", latent_ref=lref, noise_correct_step=0.5)),
+                     ("ddpm_second_flow", dict(scheduler="ddpm", latent_ref=lref, noise_correct_step=0.5, flows=flows,
+                                               guidance_rescale=0.3)),
+                     ("ddim_rescale_start2", dict(scheduler="ddim", guidance_rescale=0.5, start_time=2))):
+        out = run(**kw)
+        assert len(out["all_latent"]) == len(g[name]["all_latent"])
+        _close(out["latent"], g[name]["latent"], 1e-4)
+        _close(out["all_pred"][-1], g[name]["all_pred"][-1], 1e-4)
+        _close(out["all_latent"][0], g[name]["all_latent"][0], 1e-4)
