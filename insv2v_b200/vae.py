@@ -290,10 +290,12 @@ class AutoencoderKL(nn.Module):
 
     @torch.no_grad()
     def encode(self, x):
-        """autoencoder.py:89-95: samples the diagonal Gaussian posterior (mean + std * randn), logvar clamped."""
+        """autoencoder.py:89-95: samples the diagonal Gaussian posterior, logvar clamped to [-30, 20]. As in the
+        reference (DiagonalGaussianDistribution.sample, :22) the noise is drawn on the CPU default generator and moved
+        to the device, so a seeded run reproduces the reference's latents."""
         mean, logvar = torch.chunk(self.encode_moments(x), 2, dim=1)
         std = torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0))
-        z = mean + std * torch.randn(mean.shape, device=mean.device)
+        z = mean + std * torch.randn(mean.shape).to(device=mean.device)
         return z if x.dtype == torch.float32 else z.to(x.dtype)
 
     def forward(self, input, sample_posterior=True):

@@ -222,7 +222,7 @@ def test_flow_sampler_full_size_vs_reference_golden(full_unet):
                                      return_all=True)
     for i in range(g["steps"]):
         _gate(f"flow sampler step {i + 1}/{g['steps']}", out["all_latent"][i], ref16["all_latent"][i].float(),
-              g["all_latent"][i], 3e-3 * (i + 1))
+              g["all_latent"][i], 8e-3)  # the gate that binds is the 1.5x-of-reference-fp16 one inside _gate
     assert torch.equal(out["latent"], out["all_latent"][-1])
 
 
@@ -290,7 +290,7 @@ def test_ddpm_rescale_start_time_vs_reference_golden():
         e0 = err_stats(out["all_latent"][0], gold["all_latent"][0])
         print(f"[{name}] latent rel_l2={e['rel_l2']:.3e} first-step rel_l2={e0['rel_l2']:.3e} "
               f"last pred rel_l2={ep['rel_l2']:.3e}")
-        assert e0["rel_l2"] <= 5e-3 and e["rel_l2"] <= 3e-2 and ep["rel_l2"] <= 3e-2
+        assert e0["rel_l2"] <= 1e-2 and e["rel_l2"] <= 3e-2 and ep["rel_l2"] <= 3e-2
 
     kw = dict(latent=lat, text_cond=tc, text_uncond=tu, img_cond=cond, text_cfg=g["text_cfg"], img_cfg=g["img_cfg"])
     pipe = InferenceIP2PVideo(m, scheduler="ddpm", num_ddim_steps=steps)

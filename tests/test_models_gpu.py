@@ -1,15 +1,18 @@
 """Whole-path parity on the GPU: the drop-in UNet3DConditionModel / AutoencoderKL / sampler against the golden outputs
 of the REFERENCE's own modules (tests/golden, minted by oracle/pin_against_reference.py) on the same seeded weights and
 inputs. The product computes in fp16 storage / fp32 accumulation, the golden is fp32 CPU: per-kernel error is bounded at
-rtol 1e-3 (tests/test_kernels_gpu.py); across the ~1200-kernel network the bound asserted here is a relative L2 error
-of 1e-2 and max-abs error of 3 % of the output range (measured values are printed)."""
+rtol 1e-3 (tests/test_kernels_gpu.py); across the ~760-kernel network the bound asserted here is a relative L2 error of
+4e-3 and a max-abs error of 1 % of the output range. The bound is CALIBRATED, not assumed: tests/test_fullsize_gpu.py
+runs the reference's own fp16-autocast + SDPA path on the same GPU against the same fp32 goldens (2.0-3.0e-3 rel-L2 for
+a forward, profiles/r02_calibration.json) and requires the product to stay within 1.5x of it; measured product errors
+are 1.5-2.7e-3."""
 import pytest
 import torch
 
 from tests.helpers import err_stats, golden, schema, seeded
 
 pytestmark = pytest.mark.gpu
-REL_L2, MAX_FRAC = 1e-2, 3e-2
+REL_L2, MAX_FRAC = 4e-3, 1e-2
 
 
 def _oracle():
@@ -161,13 +164,13 @@ def test_pipeline_vs_reference_sampler_golden():
     pipe = InsV2VPipeline(m, None, num_ddim_steps=g["steps"])
     kw = dict(text_cfg=g["text_cfg"], img_cfg=g["img_cfg"])
     # errors compound over steps and are amplified by text_cfg = 7.5: 3e-2 relative L2 after 3 steps
-    _check("pipeline first clip", pipe.denoise(lat, tc, tu, cond, **kw), g["first"], rel=3e-2, frac=6e-2)
+    _check("pipeline first clip", pipe.denoise(lat, tc, tu, cond, **kw), g["first"], rel=1.2e-2, frac=2.5e-2)
     _check("pipeline second clip (mean)",
            pipe.denoise(lat, tc, tu, cond, latent_ref=lref, noise_correct_step=g["noise_correct_step"], **kw),
-           g["second_mean"], rel=3e-2, frac=6e-2)
+           g["second_mean"], rel=1.2e-2, frac=2.5e-2)
     _check("pipeline second clip (flow)",
            pipe.denoise(lat, tc, tu, cond, latent_ref=lref, noise_correct_step=g["noise_correct_step"], flows=flows,
-                        **kw), g["second_flow"], rel=3e-2, frac=6e-2)
+                        **kw), g["second_flow"], rel=1.2e-2, frac=2.5e-2)
 
 
 def test_reference_sampler_loop_runs_on_dropin_unet():
@@ -184,7 +187,7 @@ def test_reference_sampler_loop_runs_on_dropin_unet():
     def unet_fn(x, t, c):
         return m(x.cuda(), t.cuda(), encoder_hidden_states=c.cuda()).sample.cpu()
     out = O.sample_ip2p_video(unet_fn, lat, tc, tu, cond, g["text_cfg"], g["img_cfg"], g["steps"])
-    _check("reference loop on drop-in unet", out, g["first"], rel=3e-2, frac=6e-2)
+    _check("reference loop on drop-in unet", out, g["first"], rel=1.2e-2, frac=2.5e-2)
 
 
 def test_flow_utils_vs_reference_golden():
