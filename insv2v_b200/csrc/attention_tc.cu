@@ -1108,10 +1108,9 @@ static int launch_attn_pair(const CUtensorMap& tq, const CUtensorMap& tk, const 
   constexpr int smem = attnp_smem_total<NS>();
   static_assert(2 * smem <= 227 * 1024, "pair attention: two CTAs per SM must fit");
   auto kern = attention_pair_kernel<NS, POLY, MODE, DBG>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.first()) {
     IVV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
@@ -1587,14 +1586,13 @@ static int launch_attn_pair_persist(const CUtensorMap& tq, const CUtensorMap& tk
   constexpr int kPerSm = smem <= 113 * 1024 ? 2 : 1;
   static_assert(smem <= 227 * 1024, "persistent pair attention exceeds shared memory");
   auto kern = attention_pair_persist_kernel<NS, POLY>;
-  static bool configured = false;
+  static DeviceOnce configured;
   static int n_sm = 148;
-  if (!configured) {
+  if (configured.first()) {
     IVV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int dev = 0;
     IVV_CHECK_CUDA(cudaGetDevice(&dev));
     IVV_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    configured = true;
   }
   int clusters = n_sm / 2 * kPerSm;  // kPerSm CTAs per SM
   if (clusters > pp.n_items) clusters = pp.n_items;
@@ -1626,10 +1624,9 @@ static int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
                         dim3 grid, cudaStream_t stream) {
   constexpr int smem = attn2_smem_bytes<NS>();
   static_assert(smem <= 227 * 1024, "two-tile attention exceeds shared memory");
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.first()) {
     IVV_CHECK_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
   }
   IVV_CHECK_CUDA(launch_pdl(attention_tc2_kernel<NS>, grid, dim3(kAttn2Threads), smem, stream, tq, tk, tv, ap));
   return 0;
@@ -1639,11 +1636,10 @@ template <int DC, int NS>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& ap,
                        dim3 grid, cudaStream_t stream) {
   constexpr int smem = attn_smem_bytes<DC, NS>();
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.first()) {
     IVV_CHECK_CUDA(
         cudaFuncSetAttribute(attention_tc_kernel<DC, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
   }
   IVV_CHECK_CUDA(launch_pdl(attention_tc_kernel<DC, NS>, grid, dim3(kAttnThreads), smem, stream, tq, tk, tv, ap));
   return 0;

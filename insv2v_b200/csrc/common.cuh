@@ -33,6 +33,20 @@ void set_error(const char* fmt, ...);
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                   const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
+// host: "first launch of this kernel on the CURRENT device" latch. cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a
+// per-device attribute, so a process-wide `static bool` would leave a second GPU of the same process unconfigured.
+// Racy by design (two threads may both see "first": the attribute is then set twice, which is harmless).
+struct DeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 // host: programmatic dependent launch (PDL). Every kernel launched through launch_pdl() executes griddep_sync() before
 // its first global-memory access, so kernel N+1's launch latency and prologue (barrier init, TMEM alloc, descriptor
 // prefetch) overlap kernel N's tail; the chain stays ordered because each kernel only completes after its own wait.
@@ -367,6 +381,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 // one column: thread = lane/row gets the single 32-bit value at column taddr
 __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
   uint32_t r;
@@ -409,6 +429,26 @@ __device__ __forceinline__ void walk_rows(int J, int nf, long long gs, int ss, F
 #pragma unroll 4
     for (int f = f0; f < nf; f += R, g += dg, sm += dsm) fn(f, j, g, sm);
   }
+}
+
+// a += lo(packed), b += hi(packed): fp32 + fp16 in ONE instruction each (PTX add.f32.f16 -> SASS FHADD with an .H1
+// operand selector), instead of a conversion (HADD2.F32) followed by FADD. Halves the FP instruction count of the GEMM
+// epilogues' bias / residual adds.
+__device__ __forceinline__ void add_h2(float& a, float& b, uint32_t packed) {
+  asm("{\n\t"
+      ".reg .b16 lo, hi;\n\t"
+      "mov.b32 {lo, hi}, %2;\n\t"
+      "add.rn.f32.f16 %0, lo, %0;\n\t"
+      "add.rn.f32.f16 %1, hi, %1;\n\t"
+      "}"
+      : "+f"(a), "+f"(b)
+      : "r"(packed));
+}
+__device__ __forceinline__ void add_h8(float* v, const uint4& u) {
+  add_h2(v[0], v[1], u.x);
+  add_h2(v[2], v[3], u.y);
+  add_h2(v[4], v[5], u.z);
+  add_h2(v[6], v[7], u.w);
 }
 
 // ---- small math ----

@@ -852,6 +852,325 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// v3: pair kernel with a 16-warp epilogue and a dedicated store warp, for the GEMMs whose epilogue sets the pace
+// (K <= 1280 linears: attention / temporal / feed-forward out-projections, QKV, 1x1 projections; 160-wide tiles).
+//
+// What the clock64 trace of the v2 epilogue showed on the 73728x320->320 residual GEMM (profiles/r01_gemm_epilogue_
+// trace.txt): a 128x160 tile took 5 600 clk of epilogue against 1 800 clk of main loop, and most of it was not arithmetic:
+// the thread that issues the TMA stores also waited ~1 100 clk for the previous store to drain before it could request
+// the next residual tile, ~500 clk to issue three stores, ~400 clk of tile-coordinate divisions, ~300 clk for the bias
+// round trip, and group 0 carried three of the five column chunks. Here:
+//   * warp 2 is a store warp: it alone issues TMA stores, waits for their drain and requests the residual tile of the
+//     tile after next; the 16 epilogue warps never touch the TMA queue;
+//   * 16 epilogue warps (4 per TMEM lane quarter) own 40 columns each, read them with ONE pass (tcgen05.ld x32 + x8) and
+//     hand the accumulator back immediately, so all TMEM reads of a tile (1 280 clk at 64 B/clk) are in flight at once and
+//     the next main loop starts under the arithmetic;
+//   * the bias vector lives in shared memory (fp16, read as broadcast 16-byte vectors); bias and residual are added with
+//     the mixed-precision add (FHADD: fp32 + fp16 in one instruction, no conversion);
+//   * epilogue threads need no tile coordinates at all (TMA clips the store and zero-fills the residual): the N tile
+//     index is advanced by increments.
+// Roles: warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warp 2 store / residual, warp 3 idle, warps 4..19 epilogue.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kP2Threads = 640;
+constexpr int kP2BN = 160;
+constexpr int kP2Chunks = 5;                                // 32-column TMA boxes per tile (SWIZZLE_64B, 64-byte rows)
+constexpr int kP2ChunkBytes = kBlockM * 32 * 2;             // 8 KB
+constexpr int kP2SlabBytes = kP2Chunks * kP2ChunkBytes;     // 40 KB: one fp16 output tile
+constexpr int kP2BiasBytes = 8192;                          // n_out <= 4096
+constexpr int kP2StageBytes = kABytes + (kP2BN / 2) * 128;  // 16 KB activations + 10 KB half weight tile
+template <int STAGES>
+constexpr int pair160_smem_bytes() {
+  return STAGES * kP2StageBytes + 2 * kP2SlabBytes + kP2BiasBytes + 256;
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(kP2Threads, 1)
+gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
+                       const __grid_constant__ GemmKParams p, int n_tiles, int total_tiles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  constexpr uint32_t kAccStride = 256;  // TMEM columns per accumulator buffer
+  constexpr uint16_t kMask = 3;
+  uint8_t* slabs = smem + STAGES * kP2StageBytes;
+  __half* sbias = reinterpret_cast<__half*>(slabs + 2 * kP2SlabBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(slabs + 2 * kP2SlabBytes + kP2BiasBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;  // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
+  uint64_t* slab_full = tmem_empty_bar + 2;      // [2] all 16 epilogue warps have written the slab
+  uint64_t* slab_free = slab_full + 2;           // [2] the slab's store has been read out (GEMMs without residual)
+  uint64_t* res_full = slab_free + 2;            // [2] the residual tile has landed in the slab
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int crank = (int)cluster_ctarank();
+  const int tile_first = (int)cluster_id_x();
+  const int tile_step = (int)num_clusters_x();
+  const int its_per_tile = p.taps * p.kblocks;
+  const bool has_res = p.residual != nullptr && p.dbg_skip != 4;  // dbg_skip 4 (tuning): residual term dropped
+  // tuning trace (tools/gemm_trace.py): CTA 0, per tile: 0-1 producer (first / last load issued), 2-3 MMA thread
+  // (accumulator free, tile committed), 4-8 epilogue warp 4 (top, accumulator seen, in registers, slab ready, written),
+  // 9-12 store warp (slab full seen, stores issued, drained, next residual requested)
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+  auto stamp = [&](int t_, int slot) {
+    if (tracing && t_ < 32) p.trace[t_ * 16 + slot] = clock64();
+  };
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+    tma_prefetch_desc(&tmR);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);   // the leader expects the bytes of both CTAs
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 32);  // one arrive per epilogue warp of both CTAs
+      mbar_init(&slab_full[b], 16);
+      mbar_init(&slab_free[b], 1);
+      mbar_init(&res_full[b], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<2 * kAccStride>(tmem_ptr);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  griddep_sync();  // PDL: everything above overlapped the previous kernel's tail
+
+  // tile -> (N tile, pixel-box origin of this CTA's 128 rows); single-thread roles only, so the divisions are off the
+  // epilogue's path
+  auto tile_origin = [&](int tile, int& ntile, int& w0, int& h0, int& n0) {
+    ntile = tile % n_tiles;
+    const int mtile = (tile / n_tiles) * 2 + crank;
+    if (p.tiles_h == 1 && p.tiles_g == 1) {  // linear layers: a strip of rows
+      w0 = mtile * p.bw;
+      h0 = 0;
+      n0 = mtile < p.tiles_w ? 0 : p.NI;
+    } else {
+      const int tw = mtile % p.tiles_w;
+      const int th = (mtile / p.tiles_w) % p.tiles_h;
+      const int tg = mtile / (p.tiles_w * p.tiles_h);
+      w0 = tw * p.bw;
+      h0 = th * p.bh;
+      n0 = mtile < p.tiles_w * p.tiles_h * p.tiles_g ? tg * p.bn : p.NI;  // ghost tile of an odd pair: out of bounds
+    }
+  };
+
+  if (warp == 0) {
+    if (role_elect()) {
+      // ===== TMA producer: own 128 activation rows + own half of the weight tile; bytes counted on the leader =====
+      int stage = 0;
+      uint32_t phase = 0;
+      int plocal = 0;
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++plocal) {
+        int ntile, w0, h0, n0;
+        tile_origin(tile, ntile, w0, h0, n0);
+        for (int it = 0; it < its_per_tile; ++it) {
+          if (it == 0 || it == its_per_tile - 1) stamp(plocal, it == 0 ? 0 : 1);
+          const int tap = it / p.kblocks;
+          const int kb = it - tap * p.kblocks;
+          int dy = 0, dx = 0;
+          if (p.taps > 1) {
+            dy = tap / p.tap_w - (p.tap_h >> 1);
+            dx = tap % p.tap_w - (p.tap_w >> 1);
+          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kP2StageBytes;
+          const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * kP2StageBytes);
+          tma_load_4d_2sm(sa, &tmA, lead_bar, kb * kBlockK, w0 + dx, h0 + dy, n0);
+          tma_load_3d_2sm(sa + kABytes, &tmB, lead_bar, kb * kBlockK, ntile * kP2BN + crank * (kP2BN / 2), tap);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (crank == 0 && role_elect()) {
+      // ===== MMA issuer: one tcgen05.mma.cta_group::2 (M = 256, N = 160, K = 16) per 32 bytes of K =====
+      constexpr uint32_t idesc = umma_idesc_f16(2 * kBlockM, kP2BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++local) {
+        const int buf = local & 1;
+        mbar_wait(&tmem_empty_bar[buf], ((local >> 1) & 1) ^ 1);  // both CTAs' epilogue warps have read this buffer
+        tc_fence_after();
+        stamp(local, 2);
+        const uint32_t tacc = tmem_base + buf * kAccStride;
+        for (int it = 0; it < its_per_tile; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kP2StageBytes);
+          const uint64_t adesc = umma_desc_kmajor_sw128(sa);
+          const uint64_t bdesc = umma_desc_kmajor_sw128(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            if (p.dbg_skip == 1 && (it | k) != 0) continue;  // tuning only: one MMA per tile
+            umma_f16_ss_2sm(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage], kMask);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&tmem_full_bar[buf], kMask);
+        stamp(local, 3);
+      }
+    }
+  } else if (warp == 2) {
+    if (role_elect()) {
+      // ===== store warp: slab -> global (TMA store), then recycle the slab: fetch the residual tile of the tile after
+      // next into it (residual GEMMs) or declare it free =====
+      auto request_res = [&](int tile_, int s_) {
+        int ntile_, w0_, h0_, n0_;
+        tile_origin(tile_, ntile_, w0_, h0_, n0_);
+        mbar_expect_tx(&res_full[s_], kP2SlabBytes);
+        for (int chunk = 0; chunk < kP2Chunks; ++chunk)
+          tma_load_4d(slabs + s_ * kP2SlabBytes + chunk * kP2ChunkBytes, &tmR, &res_full[s_],
+                      ntile_ * kP2BN + chunk * 32, w0_, h0_, n0_);
+      };
+      if (has_res) {
+        if (tile_first < total_tiles) request_res(tile_first, 0);
+        if (tile_first + tile_step < total_tiles) request_res(tile_first + tile_step, 1);
+      }
+      int local = 0;
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++local) {
+        const int s = local & 1;
+        int ntile, w0, h0, n0;
+        tile_origin(tile, ntile, w0, h0, n0);
+        mbar_wait(&slab_full[s], (local >> 1) & 1);
+        stamp(local, 9);
+        if (p.dbg_skip != 3) {
+          for (int chunk = 0; chunk < kP2Chunks; ++chunk)
+            tma_store_4d(&tmD, slabs + s * kP2SlabBytes + chunk * kP2ChunkBytes, ntile * kP2BN + chunk * 32, w0, h0, n0);
+          bulk_commit_group();
+          stamp(local, 10);
+          bulk_wait_group_read<0>();  // only this thread waits for the drain
+        }
+        stamp(local, 11);
+        const int nxt = tile + 2 * tile_step;
+        if (has_res) {
+          if (nxt < total_tiles) request_res(nxt, s);
+        } else {
+          mbar_arrive(&slab_free[s]);
+        }
+        stamp(local, 12);
+      }
+      bulk_wait_group<0>();
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: warp e = warp - 4; TMEM lane quarter q = warp & 3 (rows 32q .. 32q+31, thread = row), column
+    // part = e >> 2 owns columns [40 part, 40 part + 40) of the tile = 16-byte vectors [5 part, 5 part + 5) =====
+    const int q = warp & 3;
+    const int part = (warp - 4) >> 2;
+    const int r = q * 32 + lane;
+    const bool has_bias = p.bias != nullptr;
+    if (has_bias) {
+      const int nvec = p.n_out >> 3;
+      for (int i = threadIdx.x - 128; i < nvec; i += 512)
+        reinterpret_cast<uint4*>(sbias)[i] = __ldg(reinterpret_cast<const uint4*>(p.bias) + i);
+    }
+    named_bar_sync(1, 512);
+    // own row of the slab: chunk c = vector / 4 at c * 8 KB, 64-byte rows, SWIZZLE_64B: 16-byte slot (cc ^ ((r >> 1) & 3))
+    const uint32_t row_off = (uint32_t)r * 64u;
+    const uint32_t sw = (uint32_t)(r >> 1) & 3u;
+    uint32_t voff[5];
+#pragma unroll
+    for (int v = 0; v < 5; ++v) {
+      const uint32_t vec = (uint32_t)part * 5u + (uint32_t)v;
+      voff[v] = (vec >> 2) * (uint32_t)kP2ChunkBytes + row_off + (((vec & 3u) ^ sw) << 4);
+    }
+    int ntile = tile_first % n_tiles;
+    const int step_n = tile_step % n_tiles;
+    const uint32_t empty_addr0 = mapa_shared(smem_u32(&tmem_empty_bar[0]), 0);
+    const uint32_t empty_addr1 = mapa_shared(smem_u32(&tmem_empty_bar[1]), 0);
+    int local = 0;
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++local) {
+      const int buf = local & 1;
+      const uint32_t ph = (local >> 1) & 1;
+      uint8_t* slab = slabs + buf * kP2SlabBytes;
+      uint4 bv[5];
+      if (has_bias) {
+        const uint4* bsrc = reinterpret_cast<const uint4*>(sbias + ntile * kP2BN + part * 40);
+#pragma unroll
+        for (int v = 0; v < 5; ++v) bv[v] = bsrc[v];
+      }
+      const bool etr = tracing && warp == 4 && lane == 0;
+      if (etr) stamp(local, 4);
+      mbar_wait(&tmem_full_bar[buf], ph);
+      tc_fence_after();
+      if (etr) stamp(local, 5);
+      const uint32_t taddr = tmem_base + buf * kAccStride + (static_cast<uint32_t>(q * 32) << 16) + part * 40;
+      uint32_t a0[32], a1[8];
+      tmem_ld32(taddr, a0);
+      tmem_ld8(taddr + 32, a1);
+      tmem_ld_wait();
+      if (etr) stamp(local, 6);
+      tc_fence_before();
+      if (lane == 0) mbar_arrive_cluster(buf ? empty_addr1 : empty_addr0);  // accumulator handed back right away
+      if (p.dbg_skip == 5) {  // tuning only: no arithmetic, nothing stored
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&slab_full[buf]);
+        ntile += step_n;
+        if (ntile >= n_tiles) ntile -= n_tiles;
+        if (has_res) mbar_wait(&res_full[buf], ph); else mbar_wait(&slab_free[buf], ph ^ 1);
+        continue;
+      }
+      if (has_res) mbar_wait(&res_full[buf], ph);   // residual landed (the fetch was issued after the slab's last store drained)
+      else mbar_wait(&slab_free[buf], ph ^ 1);      // the slab's previous store has been read out
+      if (etr) stamp(local, 7);
+#pragma unroll
+      for (int v = 0; v < 5; ++v) {
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v < 4 ? a0[v * 8 + j] : a1[j]);
+        uint4* slot = reinterpret_cast<uint4*>(slab + voff[v]);
+        if (has_bias) add_h8(x, bv[v]);
+        if (has_res) {
+          const uint4 rr = *slot;
+          add_h8(x, rr);
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = fmaxf(x[j], 0.f);
+        }
+        uint32_t pk[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          __half2 hh = __floats2half2_rn(x[2 * t], x[2 * t + 1]);
+          pk[t] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        *slot = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      if (etr) stamp(local, 8);
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store of the store warp
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&slab_full[buf]);
+      ntile += step_n;
+      if (ntile >= n_tiles) ntile -= n_tiles;
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // no CTA may exit while its peer can still signal its barriers or read its TMEM half
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc_2sm<2 * kAccStride>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 static int pow2_floor_div(long long x, int cap) {
@@ -891,14 +1210,12 @@ static void choose_box(long long W, long long H, long long NI, bool want_halo, i
   (void)pow2_ceil;
 }
 
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      n = 148;
-  }
-  return n;
+static int sm_count() {  // of the current device (cached per device ordinal)
+  static int n[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (n[dev] == 0 && cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n[dev] = 148;
+  return n[dev];
 }
 
 template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, int CS, bool TWO = false, bool HALO = false,
@@ -909,10 +1226,9 @@ static int launch_persistent_cs(const CUtensorMap& tmA, const CUtensorMap& tmB, 
   constexpr int smem = persist_smem_bytes<BN, STAGES, CW, GEGLU, TILEWIDE, TWO, HALO, DS>();
   static_assert(smem <= 227 * 1024, "persistent GEMM configuration exceeds shared memory");
   auto kern = gemm_tc_persistent_kernel<BN, STAGES, CW, GEGLU, TILEWIDE, CS, TWO, HALO, DS>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.first()) {
     IVV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
   }
   const int groups = (m_tiles + CS - 1) / CS;
   const int total = groups * n_tiles;  // (super) tiles
@@ -944,6 +1260,40 @@ static int launch_persistent_cs(const CUtensorMap& tmA, const CUtensorMap& tmB, 
   return 0;
 }
 
+template <int STAGES>
+static int launch_pair160(const CUtensorMap& tmA, const CUtensorMap& tmB2, const CUtensorMap& tmD, const CUtensorMap& tmR,
+                          const GemmKParams& kp, int m_tiles, int n_tiles, cudaStream_t stream) {
+  constexpr int smem = pair160_smem_bytes<STAGES>();
+  static_assert(smem <= 227 * 1024, "pair160 configuration exceeds shared memory");
+  auto kern = gemm_tc_pair160_kernel<STAGES>;
+  IVV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  // per device, cheap
+  const int groups = (m_tiles + 1) / 2;
+  const int total = groups * n_tiles;
+  int clusters = sm_count() / 2;
+  if (clusters > total) clusters = total;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(clusters * 2));
+  cfg.blockDim = dim3(kP2Threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = 2;
+  attr[na].val.clusterDim.y = 1;
+  attr[na].val.clusterDim.z = 1;
+  ++na;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  IVV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB2, tmD, tmR, kp, n_tiles, total));
+  return 0;
+}
+
 // cluster size 2 (weight tile multicast) whenever the M tiles pair up; IVV_CLUSTER=1 disables it (tuning hook)
 template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE>
 static int launch_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB2, const CUtensorMap& tmB1,
@@ -958,10 +1308,9 @@ template <int BN, int STAGES>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKParams& kp, int m_tiles, int n_tiles,
                   cudaStream_t stream) {
   constexpr int smem = gemm_smem_bytes<BN, STAGES>();
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.first()) {
     IVV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
   }
   dim3 grid(n_tiles, m_tiles, kp.splits);
   IVV_CHECK_CUDA(launch_pdl(gemm_tc_kernel<BN, STAGES>, grid, dim3(kGemmThreads), smem, stream, tmA, tmB, kp));
@@ -1097,7 +1446,14 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
                   persistent_ok && m_tiles >= 2 && !(getenv("IVV_DS") && atoi(getenv("IVV_DS")) == 0) &&
                   !(getenv("IVV_PAIR") && atoi(getenv("IVV_PAIR")) == 0) && getenv("IVV_CLUSTER") == nullptr &&
                   getenv("IVV_FORCE_BN") == nullptr;
-  if (ds) bn_sel = 160;
+  // v3 pair kernel (16-warp epilogue + store warp, 160-wide tiles): every short-K GEMM whose N is a multiple of 160 and
+  // that needs no per-row bias. IVV_EPI2=0 falls back to the v2 kernels (tuning hook).
+  const bool pair160 = !halo && !a->geglu && a->rowbias == nullptr && (long long)a->c * a->taps <= 1280 &&
+                       (a->n_out % 160) == 0 && a->n_out <= 4096 && persistent_ok && m_tiles >= 2 && a->splits <= 1 &&
+                       (a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0) &&
+                       !(getenv("IVV_EPI2") && atoi(getenv("IVV_EPI2")) == 0) && getenv("IVV_PAIR") == nullptr &&
+                       getenv("IVV_CLUSTER") == nullptr && getenv("IVV_FORCE_BN") == nullptr;
+  if (ds || pair160) bn_sel = 160;
   const int n_tiles = (int)((a->n_out + bn_sel - 1) / bn_sel);
 
   // ---- tensor maps ----
@@ -1120,7 +1476,7 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
 
   const bool persistent = persistent_ok && (long long)m_tiles * n_tiles < (1LL << 30);
   if (persistent) {
-    const int cw = a->geglu ? 32 : halo ? (bn_sel == 128 ? 64 : 32) : (bn_sel == 256 || bn_sel == 128) ? 64 : 32;
+    const int cw = (a->geglu || pair160) ? 32 : halo ? (bn_sel == 128 ? 64 : 32) : (bn_sel == 256 || bn_sel == 128) ? 64 : 32;
     CUtensorMap tmD, tmR;
     const uint32_t box[4] = {(uint32_t)cw, (uint32_t)kp.bw, (uint32_t)kp.bh, (uint32_t)kp.bn};
     {
@@ -1156,6 +1512,10 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
     // CTA pairs (tcgen05.mma.cta_group::2, M = 256): default whenever there are at least two M tiles
     bool pair = m_tiles >= 2 && kp.ws_stages == 0;
     if (const char* f = getenv("IVV_PAIR")) pair = pair && atoi(f) != 0;
+    if (pair160) {
+      kp.ws_stages = 0;
+      return launch_pair160<5>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
+    }
     if (ds) {
       kp.ws_stages = 0;
       return launch_persistent_cs<160, 5, 32, false, true, 2, true, false, true>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);

@@ -387,11 +387,9 @@ static int groupnorm_impl(const void* x, void* y, const void* gamma, const void*
     IVV_REQUIRE(chunks <= ws.max_chunks, "ivv_groupnorm: internal chunking error");
     dim3 grid((unsigned)chunks, (unsigned)n_bg);
     const size_t smem = (size_t)R * c * 2 * sizeof(float);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static DeviceOnce configured;  // per device (cudaFuncSetAttribute is a per-device attribute)
+    if (smem > 48 * 1024 && configured.first())
       IVV_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      configured = 96 * 1024;
-    }
     IVV_CHECK_CUDA(launch_pdl(gn_stats_kernel, grid, dim3(threads), smem, stream, reinterpret_cast<const __half*>(x),
                               ws, rows_per_bg, (int)c, groups, rows_per_cta, V, R, eps));
   }

@@ -285,11 +285,10 @@ extern "C" int ivv_temporal_attention(const void* qkv, void* o, int64_t clips, i
     while (hpc > 1 && (smem16(hpc) > 40 * 1024 || heads % hpc != 0)) --hpc;
     const size_t smem = smem16(hpc);
     IVV_REQUIRE(smem <= 200 * 1024, "ivv_temporal_attention: tile does not fit shared memory");
-    static bool configured16 = false;
-    if (!configured16) {
+    static DeviceOnce configured16;
+    if (configured16.first()) {
       IVV_CHECK_CUDA(
           cudaFuncSetAttribute(temporal_attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured16 = true;
     }
     dim3 grid((unsigned)bp, (unsigned)(heads / hpc));
     int threads = hpc * 32;
@@ -303,13 +302,12 @@ extern "C" int ivv_temporal_attention(const void* qkv, void* o, int64_t clips, i
   while (hpc > 1 && (smem_for(hpc) > 96 * 1024 || heads % hpc != 0 || hpc * frames > 1024)) --hpc;
   const size_t smem = smem_for(hpc);
   IVV_REQUIRE(smem <= 200 * 1024, "ivv_temporal_attention: tile does not fit shared memory");
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.first()) {
     IVV_CHECK_CUDA(
         cudaFuncSetAttribute(temporal_attn_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     IVV_CHECK_CUDA(
         cudaFuncSetAttribute(temporal_attn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
   }
   dim3 grid((unsigned)bp, (unsigned)(heads / hpc));
   int threads = (int)(hpc * frames);

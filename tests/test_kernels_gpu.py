@@ -74,6 +74,40 @@ def test_linear_no_residual(rows, k, n):
     report(f"linear (no residual) {rows}x{k}x{n}", out, ref)
 
 
+@pytest.mark.parametrize("rows,k,n,bias,res,relu", [
+    (4608, 1280, 3840, False, False, False),   # QKV projection, no bias: slab_free recycling path
+    (1152, 1280, 1280, True, True, False),     # 9 row tiles: odd pair count (ghost tile), residual prefetch of 2 slabs
+    (333, 320, 640, True, False, True),        # ragged last tile + ReLU
+    (20000, 640, 1920, False, True, False),    # residual without bias
+    (256, 64, 160, True, True, False),         # exactly one tile pair, one K block
+    (129, 1280, 320, True, True, False),       # second CTA of the pair holds a single valid row
+])
+def test_linear_pair160_variants(rows, k, n, bias, res, relu):
+    """The v3 pair kernel (16-warp epilogue + store warp, csrc/gemm_tc.cu gemm_tc_pair160_kernel): every combination of
+    bias / residual / ReLU, ragged and ghost tiles, and operands that are column slices of wider buffers."""
+    ops = _ops()
+    xw = h16(rows, k + 64, seed=1)
+    x = xw[:, 32:32 + k]                              # a_ld = k + 64
+    w = h16(n, k, scale=k ** -0.5, seed=2)
+    b = h16(n, seed=3) if bias else None
+    rw = h16(rows, n + 16, seed=4)
+    r = rw[:, 8:8 + n] if res else None               # res_ld = n + 16
+    ow = torch.zeros(rows, n + 24, device="cuda", dtype=torch.float16)
+    out = ops.gemm(x, ops.pack_linear(w), n_img=1, h=1, w=rows, c=k, bias=b, residual=r, relu=relu, out=ow[:, 16:16 + n])
+    ref = x.float() @ w.float().t()
+    if bias:
+        ref = ref + b.float()
+    if res:
+        ref = ref + r.float()
+    if relu:
+        ref = ref.clamp_min(0)
+    report(f"pair160 {rows}x{k}x{n} bias={bias} res={res} relu={relu}", out, ref)
+    assert float(ow[:, :16].abs().max()) == 0 and float(ow[:, 16 + n:].abs().max()) == 0  # nothing outside the window
+    # same call twice in a row on one stream (barrier phases / slab recycling across launches)
+    out2 = ops.gemm(x, ops.pack_linear(w), n_img=1, h=1, w=rows, c=k, bias=b, residual=r, relu=relu)
+    assert torch.equal(out2, out.contiguous())
+
+
 def test_linear_geglu():
     ops = _ops()
     rows, c = 500, 320

@@ -40,6 +40,9 @@ t = buf.cpu()
 t0 = int(t[t > 0].min())
 names = ["tma:first", "tma:last", "mma:acc ok", "mma:commit", "epi:top", "epi:drained", "epi:acc", "epi:res", "epi:chunks",
          "epi:bar", "epi:stored", "c0:bias req", "c0:acc regs", "c0:bias add", "c0:written"]
+if os.environ.get("IVV_EPI2", "1") != "0" and n % 160 == 0 and k <= 1280:  # v3 pair kernel (gemm_tc_pair160_kernel)
+    names = ["tma:first", "tma:last", "mma:acc ok", "mma:commit", "epi:top", "epi:acc", "epi:regs", "epi:slab ok",
+             "epi:written", "st:full", "st:issued", "st:drained", "st:res req"]
 print(f"rows={rows} k={k} n={n} res={res}  (SM clocks since the first stamp of CTA 0)")
 print("tile " + " ".join(f"{s:>11s}" for s in names))
 for g in range(32):
