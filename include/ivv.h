@@ -21,7 +21,7 @@ extern "C" {
 
 typedef void* ivv_stream_t; /* cudaStream_t */
 
-#define IVV_ABI_VERSION 3
+#define IVV_ABI_VERSION 4
 
 int ivv_abi_version(void);
 const char* ivv_last_error(void);
@@ -96,7 +96,7 @@ int ivv_attention(const void* q, int64_t q_ld, const void* k, const void* v, int
                   int64_t n_batch, int64_t s_q, int64_t s_kv, int64_t kv_div, int32_t heads, int32_t d, float scale,
                   ivv_stream_t stream);
 
-/* ---- K5: temporal self-attention over frames (HBM-bound, L = frames <= 32) ----------------------------------
+/* ---- K5: temporal self-attention over frames (HBM-bound, L = frames <= 64) ----------------------------------
  * Replaces VersatileAttention.forward core, motion_module.py:275,303-334, without either transpose copy:
  * qkv fp16 [clips*frames*hw, 3c] (q | k | v); sequences run over the frame index at fixed (clip, pixel).        */
 int ivv_temporal_attention(const void* qkv, void* o, int64_t clips, int64_t frames, int64_t hw, int64_t c,
@@ -143,6 +143,14 @@ int ivv_flow_noise_correction(const float* delta_ref, const float* flow_lat, flo
  * eps3: fp32 [3, n] (branches uncond | image | text+image); latent fp32 [n] updated in place.                   */
 int ivv_cfg_ddim_step(const float* eps3, float* latent, float* eps_out, int64_t n, float text_cfg, float img_cfg,
                       float alpha_prod_t, float alpha_prod_prev, ivv_stream_t stream);
+
+/* ---- frame I/O ------------------------------------------------------------------------
+ * ivv_frames_u8_to_f32: decoded frames uint8 [n, h, w, 3] -> fp32 [n, 3, h, w] in [-1, 1] = cv2.cvtColor(BGR2RGB)
+ * (swap_rb = 1) + ToTensor + Normalize(0.5, 0.5) of dataset/loveu_tgve_dataset.py:13-16,50-52, bit-identical.
+ * ivv_frames_to_u8: frames fp32 / fp16 [n, 3, h, w] in [-1, 1] -> uint8 [n, h, w, 3] = `x / 2 + 0.5`, `* 255`,
+ * astype(uint8) of misc_utils/image_utils.py:130,233-241 (clamped to [0, 255]).                                       */
+int ivv_frames_u8_to_f32(const void* x, float* y, int64_t n, int64_t hw, int32_t swap_rb, ivv_stream_t stream);
+int ivv_frames_to_u8(const void* x, int32_t x_is_f32, void* y, int64_t n, int64_t hw, ivv_stream_t stream);
 
 /* ---- K13b: a whole sampling step around the UNet, graph-capturable without per-step host arguments ------------------
  * The reference's loops (pl_trainer/inference/inference.py:163-219, 221-289, 313-398) do, per step: assemble the

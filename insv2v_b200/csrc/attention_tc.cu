@@ -1652,6 +1652,38 @@ static long long* g_attn_trace = nullptr;
 // stamps of its first CTA; nullptr switches tracing off
 extern "C" void ivv_debug_attn_trace(void* buf) { g_attn_trace = reinterpret_cast<long long*>(buf); }
 
+namespace ivv {
+// Tuning switches of ivv_attention, read once per process. A non-tuning build (no -DIVV_TUNING) only has the default
+// kernels: persistent CTA pairs for d <= 62, the one-tile kernel otherwise.
+struct AttnEnv {
+  int qk_first, mode, dbg;
+  bool pair, pair_short, poly, ns6, two_tile;
+};
+static const AttnEnv& attn_env() {
+  static const AttnEnv e = [] {
+    auto geti = [](const char* name, int dflt) {
+      const char* v = getenv(name);
+      return v ? atoi(v) : dflt;
+    };
+    AttnEnv a{};
+    a.qk_first = geti("IVV_ATTN_QK_FIRST", 1);
+    a.pair = geti("IVV_ATTN_PAIR", 1) != 0;
+    a.pair_short = geti("IVV_ATTN_PAIR_SHORT", 1) != 0;
+    a.poly = geti("IVV_ATTN_POLY", 0) != 0;
+    a.ns6 = geti("IVV_ATTN_NS", 2) == 6;
+#ifdef IVV_TUNING
+    a.mode = geti("IVV_ATTN_MODE", 3);
+    a.dbg = geti("IVV_ATTN_DBG", 0);
+    a.two_tile = getenv("IVV_ATTN_TWO_TILE") != nullptr;
+#else
+    a.mode = 3;
+#endif
+    return a;
+  }();
+  return e;
+}
+}  // namespace ivv
+
 extern "C" int ivv_attention(const void* q, int64_t q_ld, const void* k, const void* v, int64_t kv_ld, void* o,
                              int64_t o_ld, int64_t n_batch, int64_t s_q, int64_t s_kv, int64_t kv_div, int32_t heads,
                              int32_t d, float scale, ivv_stream_t stream_) {
@@ -1689,21 +1721,16 @@ extern "C" int ivv_attention(const void* q, int64_t q_ld, const void* k, const v
     if (int rc = make_tmap_f16(&tv, v, 4, dims, str, box, 128)) return rc;
   }
   const int dc = (d + 1 + 63) / 64;  // 64-wide chunks holding the d value columns plus the ones column
-  {
-    const char* f = getenv("IVV_ATTN_QK_FIRST");
-    ap.qk_first = f ? atoi(f) : 1;
-  }
+  const AttnEnv& env = attn_env();  // tuning switches, read from the environment ONCE (no getenv on the launch path)
+  ap.qk_first = env.qk_first;
   // CTA pairs (cta_group::2): default for d <= 62 with at least two query tiles and more than one key block;
   // IVV_ATTN_PAIR=0 falls back to the one-tile kernel, IVV_ATTN_POLY=0 keeps every exponential on the MUFU
   {
-    const char* f = getenv("IVV_ATTN_PAIR");
     // single-block problems (cross-attention, 77 keys) also go through the persistent pair kernel: its Q / O double
     // buffering overlaps one item's loads and output with the next (82 -> 55 us at S_q = 1536); IVV_ATTN_PAIR_SHORT=0
     // sends them back to the one-tile kernel
-    const char* f1 = getenv("IVV_ATTN_PAIR_SHORT");
-    const bool short_ok = s_kv > kKV || !(f1 && atoi(f1) == 0);
-    const bool pair = dc == 1 && s_q > kQ && short_ok && (reinterpret_cast<uintptr_t>(o) & 15) == 0 &&
-                      (f ? atoi(f) != 0 : true);
+    const bool short_ok = s_kv > kKV || env.pair_short;
+    const bool pair = dc == 1 && s_q > kQ && short_ok && (reinterpret_cast<uintptr_t>(o) & 15) == 0 && env.pair;
     if (pair) {
       CUtensorMap tk64;
       const uint32_t box64[4] = {64, 1, 64, 1};
@@ -1711,12 +1738,8 @@ extern "C" int ivv_attention(const void* q, int64_t q_ld, const void* k, const v
       const uint64_t str[4] = {2, (uint64_t)d * 2, (uint64_t)kv_ld * 2, (uint64_t)kv_ld * 2 * s_kv};
       if (int rc = make_tmap_f16(&tk64, k, 4, dims, str, box64, 128)) return rc;
       const unsigned tiles = (unsigned)((s_q + kQ - 1) / kQ);
-      dim3 gridp((tiles + 1) / 2 * 2, (unsigned)heads, (unsigned)n_batch);
-      const char* g = getenv("IVV_ATTN_POLY");
-      const char* h = getenv("IVV_ATTN_MODE");
-      const bool poly = g ? atoi(g) != 0 : false;
-      const int mode = h ? atoi(h) : 3;
-      if (mode == 3) {  // persistent pairs (default)
+      const bool poly = env.poly;
+      if (env.mode == 3) {  // persistent pairs (default; the only mode of a non-tuning build)
         AttnPersist pp{};
         pp.n_qpairs = (int)((tiles + 1) / 2);
         pp.heads = heads;
@@ -1727,24 +1750,23 @@ extern "C" int ivv_attention(const void* q, int64_t q_ld, const void* k, const v
           const uint64_t ostr[4] = {2, (uint64_t)d * 2, (uint64_t)o_ld * 2, (uint64_t)o_ld * 2 * s_q};
           if (int rc = make_tmap_f16(&to, o, 4, odims, ostr, box, 128)) return rc;
         }
-        const char* ns = getenv("IVV_ATTN_NS");
-        if (ns && atoi(ns) == 6) return launch_attn_pair_persist<6, 0>(tq, tk64, tv, to, ap, pp, stream);
+        if (env.ns6) return launch_attn_pair_persist<6, 0>(tq, tk64, tv, to, ap, pp, stream);
         return poly ? launch_attn_pair_persist<2, 1>(tq, tk64, tv, to, ap, pp, stream)
                     : launch_attn_pair_persist<2, 0>(tq, tk64, tv, to, ap, pp, stream);
       }
-      if (const char* dbg = getenv("IVV_ATTN_DBG")) {  // timing experiments (tools/attn_bench.py); garbage results
-        switch (atoi(dbg)) {
-          case 1: return launch_attn_pair<2, 0, 1, 1>(tq, tk64, tv, ap, gridp, stream);
-          case 2: return launch_attn_pair<2, 0, 1, 2>(tq, tk64, tv, ap, gridp, stream);
-          case 3: return launch_attn_pair<2, 0, 1, 3>(tq, tk64, tv, ap, gridp, stream);
-          case 4: return launch_attn_pair<2, 0, 1, 4>(tq, tk64, tv, ap, gridp, stream);
-          case 5: return launch_attn_pair<2, 0, 1, 5>(tq, tk64, tv, ap, gridp, stream);
-          case 6: return launch_attn_pair<2, 0, 1, 6>(tq, tk64, tv, ap, gridp, stream);
-          case 7: return launch_attn_pair<2, 0, 1, 7>(tq, tk64, tv, ap, gridp, stream);
-          default: break;
-        }
+#ifdef IVV_TUNING  // retired variants, kept for A/B timing only (build with IVV_NVCC_EXTRA=-DIVV_TUNING)
+      dim3 gridp((tiles + 1) / 2 * 2, (unsigned)heads, (unsigned)n_batch);
+      switch (env.dbg) {  // timing experiments (tools/attn_bench.py); garbage results
+        case 1: return launch_attn_pair<2, 0, 1, 1>(tq, tk64, tv, ap, gridp, stream);
+        case 2: return launch_attn_pair<2, 0, 1, 2>(tq, tk64, tv, ap, gridp, stream);
+        case 3: return launch_attn_pair<2, 0, 1, 3>(tq, tk64, tv, ap, gridp, stream);
+        case 4: return launch_attn_pair<2, 0, 1, 4>(tq, tk64, tv, ap, gridp, stream);
+        case 5: return launch_attn_pair<2, 0, 1, 5>(tq, tk64, tv, ap, gridp, stream);
+        case 6: return launch_attn_pair<2, 0, 1, 6>(tq, tk64, tv, ap, gridp, stream);
+        case 7: return launch_attn_pair<2, 0, 1, 7>(tq, tk64, tv, ap, gridp, stream);
+        default: break;
       }
-      switch (mode * 2 + (poly ? 1 : 0)) {
+      switch (env.mode * 2 + (poly ? 1 : 0)) {
         case 0: return launch_attn_pair<2, 0, 0>(tq, tk64, tv, ap, gridp, stream);
         case 1: return launch_attn_pair<2, 1, 0>(tq, tk64, tv, ap, gridp, stream);
         case 2: return launch_attn_pair<2, 0, 1>(tq, tk64, tv, ap, gridp, stream);
@@ -1752,14 +1774,17 @@ extern "C" int ivv_attention(const void* q, int64_t q_ld, const void* k, const v
         case 4: return launch_attn_pair<2, 0, 2>(tq, tk64, tv, ap, gridp, stream);
         default: return launch_attn_pair<2, 1, 2>(tq, tk64, tv, ap, gridp, stream);
       }
+#endif
     }
   }
+#ifdef IVV_TUNING
   // the two-tile kernel (K/V loads shared by 256 queries, 4-deep ring) measured equal to the one-tile kernel at
-  // S=1536, d=40 (488 vs 471 us): both are bound by the softmax warps, so it stays opt-in
-  if (dc == 1 && s_kv > 2 * kKV && s_q > kQ && getenv("IVV_ATTN_TWO_TILE") != nullptr) {
+  // S=1536, d=40 (488 vs 471 us): both are bound by the softmax warps, so it stays a tuning variant
+  if (dc == 1 && s_kv > 2 * kKV && s_q > kQ && env.two_tile) {
     dim3 grid2((unsigned)((s_q + 2 * kQ - 1) / (2 * kQ)), (unsigned)heads, (unsigned)n_batch);
     return launch_attn2<4>(tq, tk, tv, ap, grid2, stream);
   }
+#endif
   dim3 grid((unsigned)((s_q + kQ - 1) / kQ), (unsigned)heads, (unsigned)n_batch);
   if (dc == 1) return launch_attn<1, 2>(tq, tk, tv, ap, grid, stream);
   if (dc == 2) return launch_attn<2, 2>(tq, tk, tv, ap, grid, stream);

@@ -187,6 +187,41 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
   }
 }
 
+// ---- frame I/O -------------------------------------------------------------------------
+// decoded video frames, uint8 [n, h, w, 3] (cv2: BGR) -> fp32 [n, 3, h, w] in [-1, 1]: cv2.cvtColor(BGR2RGB) +
+// transforms.ToTensor() (x / 255) + Normalize(0.5, 0.5) ((t - 0.5) / 0.5) of dataset/loveu_tgve_dataset.py:13-16,50-52,
+// with the same operation order (two IEEE divisions, one subtraction), so the result is bit-identical.
+__global__ void u8hwc_to_f32chw_kernel(const uint8_t* __restrict__ x, float* __restrict__ y, long long n, long long hw,
+                                       int swap_rb) {
+  const long long total = n * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / hw, pix = i % hw;
+    const uint8_t* src = x + i * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float t = __fdiv_rn((float)src[swap_rb ? 2 - c : c], 255.f);
+      y[(img * 3 + c) * hw + pix] = __fdiv_rn(__fsub_rn(t, 0.5f), 0.5f);
+    }
+  }
+}
+
+// edited frames fp32 / fp16 [n, 3, h, w] in [-1, 1] -> uint8 [n, h, w, 3]: `x / 2 + 0.5`, `* 255`, astype(uint8)
+// (misc_utils/image_utils.py:130,233-235: float32 arithmetic in that order, truncation; values outside [0, 255] are
+// clamped here, where numpy's cast would wrap - callers clip to [-1, 1] first, insv2v_run_loveu_tgve.py:165)
+template <typename T>
+__global__ void chw_to_u8hwc_kernel(const T* __restrict__ x, uint8_t* __restrict__ y, long long n, long long hw) {
+  const long long total = n * hw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long img = i / hw, pix = i % hw;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = (float)x[(img * 3 + c) * hw + pix];
+      const float u = __fmul_rn(__fadd_rn(__fmul_rn(v, 0.5f), 0.5f), 255.f);
+      y[i * 3 + c] = (uint8_t)fminf(fmaxf(u, 0.f), 255.f);
+    }
+  }
+}
+
 static inline unsigned grid_for(long long total, int threads) {
   long long b = (total + threads - 1) / threads;
   const long long cap = 148LL * 16;
@@ -318,6 +353,27 @@ extern "C" int ivv_cfg_ddim_step(const float* eps3, float* latent, float* eps_ou
   cfg_ddim_kernel<<<grid_for(n, 256), 256, 0, STREAM>>>(eps3, latent, eps_out, n, text_cfg, img_cfg,
                                                         sqrtf(alpha_prod_t), sqrtf(1.f - alpha_prod_t),
                                                         sqrtf(alpha_prod_prev), sqrtf(1.f - alpha_prod_prev));
+  IVV_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ivv_frames_u8_to_f32(const void* x, float* y, int64_t n, int64_t hw, int32_t swap_rb,
+                                    ivv_stream_t stream_) {
+  IVV_REQUIRE(x && y && n > 0 && hw > 0, "ivv_frames_u8_to_f32: bad arguments");
+  u8hwc_to_f32chw_kernel<<<grid_for(n * hw, 256), 256, 0, STREAM>>>(reinterpret_cast<const uint8_t*>(x), y, n, hw,
+                                                                  swap_rb);
+  IVV_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int ivv_frames_to_u8(const void* x, int32_t x_is_f32, void* y, int64_t n, int64_t hw, ivv_stream_t stream_) {
+  IVV_REQUIRE(x && y && n > 0 && hw > 0, "ivv_frames_to_u8: bad arguments");
+  if (x_is_f32)
+    chw_to_u8hwc_kernel<float><<<grid_for(n * hw, 256), 256, 0, STREAM>>>(reinterpret_cast<const float*>(x),
+                                                                          reinterpret_cast<uint8_t*>(y), n, hw);
+  else
+    chw_to_u8hwc_kernel<__half><<<grid_for(n * hw, 256), 256, 0, STREAM>>>(reinterpret_cast<const __half*>(x),
+                                                                           reinterpret_cast<uint8_t*>(y), n, hw);
   IVV_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

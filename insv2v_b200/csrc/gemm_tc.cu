@@ -877,13 +877,22 @@ constexpr int kP2Chunks = 5;                                // 32-column TMA box
 constexpr int kP2ChunkBytes = kBlockM * 32 * 2;             // 8 KB
 constexpr int kP2SlabBytes = kP2Chunks * kP2ChunkBytes;     // 40 KB: one fp16 output tile
 constexpr int kP2BiasBytes = 8192;                          // n_out <= 4096
-constexpr int kP2StageBytes = kABytes + (kP2BN / 2) * 128;  // 16 KB activations + 10 KB half weight tile
-template <int STAGES>
+constexpr int kP2BTileBytes = (kP2BN / 2) * 128;            // 10 KB: this CTA's half of a 160 x 64 weight tile
+constexpr int kP2StageBytes = kABytes + kP2BTileBytes;      // 16 KB activations + 10 KB half weight tile
+constexpr int kP2WsKBlocks = 5;                             // weight-stationary mode: K <= 320
+template <int STAGES, bool WS>
 constexpr int pair160_smem_bytes() {
-  return STAGES * kP2StageBytes + 2 * kP2SlabBytes + kP2BiasBytes + 256;
+  return (WS ? STAGES * kABytes + kP2WsKBlocks * kP2BTileBytes : STAGES * kP2StageBytes) + 2 * kP2SlabBytes +
+         kP2BiasBytes + 256;
 }
 
-template <int STAGES>
+// WS (weight-stationary, K <= 320): these GEMMs are bound by what the SM can pull through TMA (knock-outs in
+// profiles/r02_gemm_pair160_knockouts.txt: time follows bytes moved per tile: 133 KB operands + 40 KB residual + 40 KB
+// store; removing the MMAs changes nothing). The weight half-tile of a CTA (all of K: <= 50 KB) therefore stays resident
+// in shared memory and only activations stream: 82 KB instead of 133 KB of operands per tile. To keep one N tile per
+// cluster for as long as possible, the (N tile, M pair) units are walked N-major and each cluster takes a contiguous
+// range; the weights are reloaded only where a range crosses into the next N tile.
+template <int STAGES, bool WS>
 __global__ void __launch_bounds__(kP2Threads, 1)
 gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
@@ -892,7 +901,9 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   constexpr uint32_t kAccStride = 256;  // TMEM columns per accumulator buffer
   constexpr uint16_t kMask = 3;
-  uint8_t* slabs = smem + STAGES * kP2StageBytes;
+  constexpr int kOperandBytes = WS ? STAGES * kABytes + kP2WsKBlocks * kP2BTileBytes : STAGES * kP2StageBytes;
+  uint8_t* b_res = smem + STAGES * kABytes;  // WS only: [k block][80 weight rows x 128 B]
+  uint8_t* slabs = smem + kOperandBytes;
   __half* sbias = reinterpret_cast<__half*>(slabs + 2 * kP2SlabBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(slabs + 2 * kP2SlabBytes + kP2BiasBytes);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -901,13 +912,20 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint64_t* slab_full = tmem_empty_bar + 2;      // [2] all 16 epilogue warps have written the slab
   uint64_t* slab_free = slab_full + 2;           // [2] the slab's store has been read out (GEMMs without residual)
   uint64_t* res_full = slab_free + 2;            // [2] the residual tile has landed in the slab
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 2);
+  uint64_t* b_full = res_full + 2;               // WS: resident weights landed (leader counts both CTAs' bytes)
+  uint64_t* b_free = b_full + 1;                 // WS: every MMA that read the resident weights has completed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_free + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int crank = (int)cluster_ctarank();
-  const int tile_first = (int)cluster_id_x();
-  const int tile_step = (int)num_clusters_x();
+  const int n_clusters = (int)num_clusters_x();
+  const int cid = (int)cluster_id_x();
+  const int groups = total_tiles / n_tiles;  // M-tile pairs
+  // units of this cluster: WS -> contiguous range of the N-major order; else round robin over the M-major order
+  const int u_begin = WS ? (int)((long long)cid * total_tiles / n_clusters) : cid;
+  const int u_end = WS ? (int)((long long)(cid + 1) * total_tiles / n_clusters) : total_tiles;
+  const int u_step = WS ? 1 : n_clusters;
   const int its_per_tile = p.taps * p.kblocks;
   const bool has_res = p.residual != nullptr && p.dbg_skip != 4;  // dbg_skip 4 (tuning): residual term dropped
   // tuning trace (tools/gemm_trace.py): CTA 0, per tile: 0-1 producer (first / last load issued), 2-3 MMA thread
@@ -934,6 +952,8 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       mbar_init(&slab_free[b], 1);
       mbar_init(&res_full[b], 1);
     }
+    mbar_init(b_full, 1);
+    mbar_init(b_free, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2sm<2 * kAccStride>(tmem_ptr);
@@ -943,11 +963,19 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const uint32_t tmem_base = *tmem_ptr;
   griddep_sync();  // PDL: everything above overlapped the previous kernel's tail
 
-  // tile -> (N tile, pixel-box origin of this CTA's 128 rows); single-thread roles only, so the divisions are off the
-  // epilogue's path
-  auto tile_origin = [&](int tile, int& ntile, int& w0, int& h0, int& n0) {
-    ntile = tile % n_tiles;
-    const int mtile = (tile / n_tiles) * 2 + crank;
+  // unit -> (N tile, M pair); single-thread roles only (the epilogue warps advance the N tile by increments)
+  auto decode = [&](int u, int& ntile, int& mg) {
+    if (WS) {
+      ntile = u / groups;
+      mg = u - ntile * groups;
+    } else {
+      ntile = u % n_tiles;
+      mg = u / n_tiles;
+    }
+  };
+  // pixel-box origin of this CTA's 128 rows of M pair mg
+  auto origin = [&](int mg, int& w0, int& h0, int& n0) {
+    const int mtile = mg * 2 + crank;
     if (p.tiles_h == 1 && p.tiles_g == 1) {  // linear layers: a strip of rows
       w0 = mtile * p.bw;
       h0 = 0;
@@ -968,9 +996,25 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       int plocal = 0;
-      for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++plocal) {
-        int ntile, w0, h0, n0;
-        tile_origin(tile, ntile, w0, h0, n0);
+      int cur_nt = -1;
+      uint32_t bfree_par = 0;
+      for (int u = u_begin; u < u_end; u += u_step, ++plocal) {
+        int ntile, mg, w0, h0, n0;
+        decode(u, ntile, mg);
+        origin(mg, w0, h0, n0);
+        if constexpr (WS) {
+          if (ntile != cur_nt) {
+            if (cur_nt >= 0) {  // the MMAs of the previous N tile must be done with the resident weights
+              mbar_wait(b_free, bfree_par);
+              bfree_par ^= 1;
+            }
+            const uint32_t lead_b = mapa_shared(smem_u32(b_full), 0);
+            if (crank == 0) mbar_expect_tx(b_full, 2 * its_per_tile * kP2BTileBytes);
+            for (int it = 0; it < its_per_tile; ++it)
+              tma_load_3d_2sm(b_res + it * kP2BTileBytes, &tmB, lead_b, it * kBlockK, ntile * kP2BN + crank * (kP2BN / 2), 0);
+            cur_nt = ntile;
+          }
+        }
         for (int it = 0; it < its_per_tile; ++it) {
           if (it == 0 || it == its_per_tile - 1) stamp(plocal, it == 0 ? 0 : 1);
           const int tap = it / p.kblocks;
@@ -981,11 +1025,16 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             dx = tap % p.tap_w - (p.tap_w >> 1);
           }
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * kP2StageBytes;
           const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
-          if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * kP2StageBytes);
-          tma_load_4d_2sm(sa, &tmA, lead_bar, kb * kBlockK, w0 + dx, h0 + dy, n0);
-          tma_load_3d_2sm(sa + kABytes, &tmB, lead_bar, kb * kBlockK, ntile * kP2BN + crank * (kP2BN / 2), tap);
+          if constexpr (WS) {
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * kABytes);
+            tma_load_4d_2sm(smem + stage * kABytes, &tmA, lead_bar, kb * kBlockK, w0 + dx, h0 + dy, n0);
+          } else {
+            uint8_t* sa = smem + stage * kP2StageBytes;
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * kP2StageBytes);
+            tma_load_4d_2sm(sa, &tmA, lead_bar, kb * kBlockK, w0 + dx, h0 + dy, n0);
+            tma_load_3d_2sm(sa + kABytes, &tmB, lead_bar, kb * kBlockK, ntile * kP2BN + crank * (kP2BN / 2), tap);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -1000,8 +1049,19 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++local) {
+      int cur_nt = -1;
+      uint32_t bfull_par = 0;
+      for (int u = u_begin; u < u_end; u += u_step, ++local) {
         const int buf = local & 1;
+        if constexpr (WS) {
+          int ntile, mg;
+          decode(u, ntile, mg);
+          if (ntile != cur_nt) {
+            mbar_wait(b_full, bfull_par);
+            bfull_par ^= 1;
+            cur_nt = ntile;
+          }
+        }
         mbar_wait(&tmem_empty_bar[buf], ((local >> 1) & 1) ^ 1);  // both CTAs' epilogue warps have read this buffer
         tc_fence_after();
         stamp(local, 2);
@@ -1009,9 +1069,9 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         for (int it = 0; it < its_per_tile; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * kP2StageBytes);
+          const uint32_t sa = smem_u32(smem + stage * (WS ? kABytes : kP2StageBytes));
           const uint64_t adesc = umma_desc_kmajor_sw128(sa);
-          const uint64_t bdesc = umma_desc_kmajor_sw128(sa + kABytes);
+          const uint64_t bdesc = umma_desc_kmajor_sw128(WS ? smem_u32(b_res + it * kP2BTileBytes) : sa + kABytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             if (p.dbg_skip == 1 && (it | k) != 0) continue;  // tuning only: one MMA per tile
@@ -1024,6 +1084,11 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           }
         }
         umma_commit_2sm(&tmem_full_bar[buf], kMask);
+        if constexpr (WS) {
+          // last unit of this N tile: once these MMAs retire, both producers may overwrite the resident weights
+          const int un = u + u_step;
+          if (un < u_end && un / groups != cur_nt) umma_commit_2sm(b_free, kMask);
+        }
         stamp(local, 3);
       }
     }
@@ -1031,23 +1096,25 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (role_elect()) {
       // ===== store warp: slab -> global (TMA store), then recycle the slab: fetch the residual tile of the tile after
       // next into it (residual GEMMs) or declare it free =====
-      auto request_res = [&](int tile_, int s_) {
-        int ntile_, w0_, h0_, n0_;
-        tile_origin(tile_, ntile_, w0_, h0_, n0_);
+      auto request_res = [&](int u_, int s_) {
+        int ntile_, mg_, w0_, h0_, n0_;
+        decode(u_, ntile_, mg_);
+        origin(mg_, w0_, h0_, n0_);
         mbar_expect_tx(&res_full[s_], kP2SlabBytes);
         for (int chunk = 0; chunk < kP2Chunks; ++chunk)
           tma_load_4d(slabs + s_ * kP2SlabBytes + chunk * kP2ChunkBytes, &tmR, &res_full[s_],
                       ntile_ * kP2BN + chunk * 32, w0_, h0_, n0_);
       };
       if (has_res) {
-        if (tile_first < total_tiles) request_res(tile_first, 0);
-        if (tile_first + tile_step < total_tiles) request_res(tile_first + tile_step, 1);
+        if (u_begin < u_end) request_res(u_begin, 0);
+        if (u_begin + u_step < u_end) request_res(u_begin + u_step, 1);
       }
       int local = 0;
-      for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++local) {
+      for (int u = u_begin; u < u_end; u += u_step, ++local) {
         const int s = local & 1;
-        int ntile, w0, h0, n0;
-        tile_origin(tile, ntile, w0, h0, n0);
+        int ntile, mg, w0, h0, n0;
+        decode(u, ntile, mg);
+        origin(mg, w0, h0, n0);
         mbar_wait(&slab_full[s], (local >> 1) & 1);
         stamp(local, 9);
         if (p.dbg_skip != 3) {
@@ -1058,9 +1125,9 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           bulk_wait_group_read<0>();  // only this thread waits for the drain
         }
         stamp(local, 11);
-        const int nxt = tile + 2 * tile_step;
+        const int nxt = u + 2 * u_step;
         if (has_res) {
-          if (nxt < total_tiles) request_res(nxt, s);
+          if (nxt < u_end) request_res(nxt, s);
         } else {
           mbar_arrive(&slab_free[s]);
         }
@@ -1090,12 +1157,14 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const uint32_t vec = (uint32_t)part * 5u + (uint32_t)v;
       voff[v] = (vec >> 2) * (uint32_t)kP2ChunkBytes + row_off + (((vec & 3u) ^ sw) << 4);
     }
-    int ntile = tile_first % n_tiles;
-    const int step_n = tile_step % n_tiles;
+    // N tile of the current unit, advanced by increments (no per-tile division on this path)
+    int ntile, mg;
+    decode(u_begin < u_end ? u_begin : 0, ntile, mg);
+    const int step_n = n_clusters % n_tiles;
     const uint32_t empty_addr0 = mapa_shared(smem_u32(&tmem_empty_bar[0]), 0);
     const uint32_t empty_addr1 = mapa_shared(smem_u32(&tmem_empty_bar[1]), 0);
     int local = 0;
-    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++local) {
+    for (int u = u_begin; u < u_end; u += u_step, ++local) {
       const int buf = local & 1;
       const uint32_t ph = (local >> 1) & 1;
       uint8_t* slab = slabs + buf * kP2SlabBytes;
@@ -1104,6 +1173,15 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const uint4* bsrc = reinterpret_cast<const uint4*>(sbias + ntile * kP2BN + part * 40);
 #pragma unroll
         for (int v = 0; v < 5; ++v) bv[v] = bsrc[v];
+      }
+      if constexpr (WS) {
+        if (++mg == groups) {
+          mg = 0;
+          ++ntile;
+        }
+      } else {
+        ntile += step_n;
+        if (ntile >= n_tiles) ntile -= n_tiles;
       }
       const bool etr = tracing && warp == 4 && lane == 0;
       if (etr) stamp(local, 4);
@@ -1118,46 +1196,38 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (etr) stamp(local, 6);
       tc_fence_before();
       if (lane == 0) mbar_arrive_cluster(buf ? empty_addr1 : empty_addr0);  // accumulator handed back right away
-      if (p.dbg_skip == 5) {  // tuning only: no arithmetic, nothing stored
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&slab_full[buf]);
-        ntile += step_n;
-        if (ntile >= n_tiles) ntile -= n_tiles;
-        if (has_res) mbar_wait(&res_full[buf], ph); else mbar_wait(&slab_free[buf], ph ^ 1);
-        continue;
-      }
       if (has_res) mbar_wait(&res_full[buf], ph);   // residual landed (the fetch was issued after the slab's last store drained)
       else mbar_wait(&slab_free[buf], ph ^ 1);      // the slab's previous store has been read out
       if (etr) stamp(local, 7);
+      if (p.dbg_skip != 5) {  // dbg_skip 5 (tuning): no arithmetic, nothing written
 #pragma unroll
-      for (int v = 0; v < 5; ++v) {
-        float x[8];
+        for (int v = 0; v < 5; ++v) {
+          float x[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v < 4 ? a0[v * 8 + j] : a1[j]);
-        uint4* slot = reinterpret_cast<uint4*>(slab + voff[v]);
-        if (has_bias) add_h8(x, bv[v]);
-        if (has_res) {
-          const uint4 rr = *slot;
-          add_h8(x, rr);
+          for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v < 4 ? a0[v * 8 + j] : a1[j]);
+          uint4* slot = reinterpret_cast<uint4*>(slab + voff[v]);
+          if (has_bias) add_h8(x, bv[v]);
+          if (has_res) {
+            const uint4 rr = *slot;
+            add_h8(x, rr);
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) x[j] = fmaxf(x[j], 0.f);
+          }
+          uint32_t pk[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            __half2 hh = __floats2half2_rn(x[2 * t], x[2 * t + 1]);
+            pk[t] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+          *slot = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = fmaxf(x[j], 0.f);
-        }
-        uint32_t pk[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          __half2 hh = __floats2half2_rn(x[2 * t], x[2 * t + 1]);
-          pk[t] = *reinterpret_cast<uint32_t*>(&hh);
-        }
-        *slot = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       if (etr) stamp(local, 8);
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store of the store warp
       __syncwarp();
       if (lane == 0) mbar_arrive(&slab_full[buf]);
-      ntile += step_n;
-      if (ntile >= n_tiles) ntile -= n_tiles;
     }
   }
 
@@ -1260,13 +1330,14 @@ static int launch_persistent_cs(const CUtensorMap& tmA, const CUtensorMap& tmB, 
   return 0;
 }
 
-template <int STAGES>
+template <int STAGES, bool WS>
 static int launch_pair160(const CUtensorMap& tmA, const CUtensorMap& tmB2, const CUtensorMap& tmD, const CUtensorMap& tmR,
                           const GemmKParams& kp, int m_tiles, int n_tiles, cudaStream_t stream) {
-  constexpr int smem = pair160_smem_bytes<STAGES>();
+  constexpr int smem = pair160_smem_bytes<STAGES, WS>();
   static_assert(smem <= 227 * 1024, "pair160 configuration exceeds shared memory");
-  auto kern = gemm_tc_pair160_kernel<STAGES>;
-  IVV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  // per device, cheap
+  auto kern = gemm_tc_pair160_kernel<STAGES, WS>;
+  static DeviceOnce configured;
+  if (configured.first()) IVV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int groups = (m_tiles + 1) / 2;
   const int total = groups * n_tiles;
   int clusters = sm_count() / 2;
@@ -1319,6 +1390,34 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKPar
 
 }  // namespace ivv
 
+namespace ivv {
+// Tuning switches of ivv_gemm, read from the environment ONCE per process (getenv is not on the launch path).
+// -1 = unset. IVV_HALO / IVV_DS / IVV_EPI2 / IVV_PAIR: 0 disables; IVV_CLUSTER=2, IVV_FORCE_BN=32|64|128|160|256,
+// IVV_NO_WS=1, IVV_DEBUG_SKIP=1..5 (knock-outs, results are garbage).
+struct GemmEnv {
+  int halo, ds, epi2, pair, cluster, force_bn, no_ws, dbg_skip;
+};
+static const GemmEnv& gemm_env() {
+  static const GemmEnv e = [] {
+    auto geti = [](const char* name) {
+      const char* v = getenv(name);
+      return v ? atoi(v) : -1;
+    };
+    GemmEnv g{};
+    g.halo = geti("IVV_HALO");
+    g.ds = geti("IVV_DS");
+    g.epi2 = geti("IVV_EPI2");
+    g.pair = geti("IVV_PAIR");
+    g.cluster = geti("IVV_CLUSTER");
+    g.force_bn = geti("IVV_FORCE_BN");
+    g.no_ws = geti("IVV_NO_WS");
+    g.dbg_skip = geti("IVV_DEBUG_SKIP");
+    return g;
+  }();
+  return e;
+}
+}  // namespace ivv
+
 // tuning / test hook (not in ivv.h): the pixel box ivv_gemm picks for a [n_img, h, w] activation, and whether the halo
 // kernel accepts it (box inside one frame, whole swizzle atoms per box row, (bh + 2) * bw <= 160)
 extern "C" int ivv_debug_conv_box(int64_t w, int64_t h, int64_t n_img, int32_t want_halo, int32_t* bw, int32_t* bh,
@@ -1357,9 +1456,10 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
   IVV_REQUIRE(!(a->geglu && (a->rowbias || a->residual)), "ivv_gemm: GEGLU epilogue takes bias only");
 
   GemmKParams kp{};
+  const GemmEnv& env = gemm_env();
   // 3x3 convolutions on fp16 outputs may take the halo kernel (one activation box per filter column); IVV_HALO=0 disables
   const bool want_halo = a->taps == 9 && tap_h == 3 && tap_w == 3 && !a->geglu && !a->out_f32 && a->splits <= 1 &&
-                         !(getenv("IVV_HALO") && atoi(getenv("IVV_HALO")) == 0);
+                         env.halo != 0;
   choose_box(a->w, a->h, a->n_img, want_halo, &kp.bw, &kp.bh, &kp.bn);
   kp.halo_bytes = (kp.bh + 2) * kp.bw * 128;
   kp.trace = g_gemm_trace;
@@ -1378,7 +1478,7 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
   kp.geglu = a->geglu;
   kp.out_cols = a->geglu ? (int)(a->n_out / 2) : (int)a->n_out;
   kp.out_f32 = a->out_f32;
-  if (const char* f = getenv("IVV_DEBUG_SKIP")) kp.dbg_skip = atoi(f);
+  if (env.dbg_skip >= 0) kp.dbg_skip = env.dbg_skip;
   kp.splits = a->splits > 1 ? a->splits : 1;
   kp.split_stride = (long long)a->n_img * a->h * a->w * a->d_ld;
   if (kp.splits > 1) {
@@ -1405,8 +1505,7 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
   const bool persistent_ok = !a->out_f32 && (a->d_ld % 8) == 0 && ((reinterpret_cast<uintptr_t>(a->d) & 15) == 0) && res_ok;
   // the halo kernel is a pair-mode persistent kernel with 128/160/256-wide tiles
   const bool halo = want_halo && halo_box_ok(kp.bw, kp.bh, kp.bn) && persistent_ok && m_tiles >= 2 && a->n_out >= 96 &&
-                    !(getenv("IVV_PAIR") && atoi(getenv("IVV_PAIR")) == 0) && getenv("IVV_CLUSTER") == nullptr &&
-                    getenv("IVV_FORCE_BN") == nullptr;
+                    env.pair != 0 && env.cluster < 0 && env.force_bn < 0;
 
   // ---- tile-N choice: least padding first, then enough CTAs to fill 148 SMs ----
   int bn_sel;
@@ -1434,8 +1533,8 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
     }
   }
   if (!a->geglu) {  // tuning hook (tools/tile_sweep.py): IVV_FORCE_BN=32|64|128|160|256
-    if (const char* f = getenv("IVV_FORCE_BN")) {
-      const int v = atoi(f);
+    if (env.force_bn >= 0) {
+      const int v = env.force_bn;
       if (v == 32 || v == 64 || v == 128 || v == 160 || v == 256) bn_sel = v;
     }
   }
@@ -1443,16 +1542,13 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
   // two staging slabs and 160-wide tiles, so the residual fetch of the next tile overlaps this tile's epilogue.
   // IVV_DS=0 disables (tuning hook).
   const bool ds = a->residual != nullptr && !halo && !a->geglu && a->taps == 1 && a->c <= 640 && (a->n_out % 160) == 0 &&
-                  persistent_ok && m_tiles >= 2 && !(getenv("IVV_DS") && atoi(getenv("IVV_DS")) == 0) &&
-                  !(getenv("IVV_PAIR") && atoi(getenv("IVV_PAIR")) == 0) && getenv("IVV_CLUSTER") == nullptr &&
-                  getenv("IVV_FORCE_BN") == nullptr;
+                  persistent_ok && m_tiles >= 2 && env.ds != 0 && env.pair != 0 && env.cluster < 0 && env.force_bn < 0;
   // v3 pair kernel (16-warp epilogue + store warp, 160-wide tiles): every short-K GEMM whose N is a multiple of 160 and
   // that needs no per-row bias. IVV_EPI2=0 falls back to the v2 kernels (tuning hook).
   const bool pair160 = !halo && !a->geglu && a->rowbias == nullptr && (long long)a->c * a->taps <= 1280 &&
                        (a->n_out % 160) == 0 && a->n_out <= 4096 && persistent_ok && m_tiles >= 2 && a->splits <= 1 &&
                        (a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0) &&
-                       !(getenv("IVV_EPI2") && atoi(getenv("IVV_EPI2")) == 0) && getenv("IVV_PAIR") == nullptr &&
-                       getenv("IVV_CLUSTER") == nullptr && getenv("IVV_FORCE_BN") == nullptr;
+                       env.epi2 != 0 && env.pair < 0 && env.cluster < 0 && env.force_bn < 0;
   if (ds || pair160) bn_sel = 160;
   const int n_tiles = (int)((a->n_out + bn_sel - 1) / bn_sel);
 
@@ -1497,7 +1593,7 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
     // 2-CTA clusters with a TMA-multicast weight tile: measured neutral (tools/profile_ops.py with IVV_CLUSTER=2) — the
     // limit is the ~60 B/clk each SM can ingest, which multicast does not reduce — so it is opt-in.
     int cs = 1;
-    if (const char* f = getenv("IVV_CLUSTER")) cs = (atoi(f) == 2 && m_tiles >= 2) ? 2 : 1;
+    if (env.cluster >= 0) cs = (env.cluster == 2 && m_tiles >= 2) ? 2 : 1;
     // Weight-stationary mode for short-K GEMMs with many M tiles (the K = 320 linears of the 32x48 level): the weight
     // tile of a CTA (all of K) stays in shared memory, only activations stream -> 2.25x less operand ingest per tile.
     {
@@ -1506,15 +1602,18 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
       const long long b_res = (long long)kp.taps * kp.kblocks * bn_sel * 128;
       const long long a_slots = (region - b_res) / kABytes;
       const bool ws_ok = !a->geglu && bn_sel >= 128 && a_slots >= 4 && n_tiles <= sm_count() / 2 &&
-                         (long long)m_tiles * n_tiles >= 4LL * sm_count() && getenv("IVV_NO_WS") == nullptr;
+                         (long long)m_tiles * n_tiles >= 4LL * sm_count() && env.no_ws < 0;
       kp.ws_stages = ws_ok ? (int)(a_slots < stages ? a_slots : stages) : 0;
     }
     // CTA pairs (tcgen05.mma.cta_group::2, M = 256): default whenever there are at least two M tiles
     bool pair = m_tiles >= 2 && kp.ws_stages == 0;
-    if (const char* f = getenv("IVV_PAIR")) pair = pair && atoi(f) != 0;
+    if (env.pair >= 0) pair = pair && env.pair != 0;
     if (pair160) {
       kp.ws_stages = 0;
-      return launch_pair160<5>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
+      // weight-stationary whenever all of K fits beside the rings (K <= 320, linear); IVV_NO_WS=1 disables (tuning hook)
+      if (a->taps == 1 && kp.kblocks <= kP2WsKBlocks && env.no_ws < 0)
+        return launch_pair160<5, true>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
+      return launch_pair160<5, false>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
     }
     if (ds) {
       kp.ws_stages = 0;

@@ -1,4 +1,5 @@
-// Temporal self-attention over the frame axis (AnimateDiff motion module), L = frames <= 32.
+// Temporal self-attention over the frame axis (AnimateDiff motion module), L = frames <= 64 (the reference's config
+// has temporal_position_encoding_max_len = 32; 64 serves the long-form [3,8,64,48,72] capture of BASELINE configs[4]).
 // HBM-bound: 0.1 % of the UNet FLOPs but 4 full activation passes. The reference transposes (b f) d c -> (b d) f c
 // and back around SDPA (motion_module.py:275,334); here the sequence is gathered with a frame stride straight from the
 // fused q|k|v projection and written back in token order, so neither transpose copy exists.
@@ -11,7 +12,7 @@
 namespace ivv {
 
 constexpr int kTPad = 8;       // halfs of row padding: 16-byte reads of consecutive frames hit distinct banks
-constexpr int kMaxFrames = 32;
+constexpr int kMaxFrames = 64;
 
 // 16-byte asynchronous global -> shared copy (LDGSTS); src_bytes = 0 zero-fills the destination. The gather of a
 // sequence is 16 x 3 scattered row segments: issued as plain load/store pairs each thread waits for one HBM round trip
@@ -270,7 +271,7 @@ extern "C" int ivv_temporal_attention(const void* qkv, void* o, int64_t clips, i
   using namespace ivv;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   IVV_REQUIRE(qkv && o && clips > 0 && frames > 0 && hw > 0 && c > 0 && heads > 0, "ivv_temporal_attention: bad args");
-  IVV_REQUIRE(frames <= kMaxFrames, "ivv_temporal_attention: frames (%lld) must be <= 32", (long long)frames);
+  IVV_REQUIRE(frames <= kMaxFrames, "ivv_temporal_attention: frames (%lld) must be <= 64", (long long)frames);
   IVV_REQUIRE(c % heads == 0 && (c / heads) % 8 == 0 && (c / heads) <= 256,
               "ivv_temporal_attention: head dim %lld must be a multiple of 8 and <= 256", (long long)(c / heads));
   const int d = (int)(c / heads);
@@ -308,6 +309,8 @@ extern "C" int ivv_temporal_attention(const void* qkv, void* o, int64_t clips, i
         cudaFuncSetAttribute(temporal_attn_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     IVV_CHECK_CUDA(
         cudaFuncSetAttribute(temporal_attn_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    IVV_CHECK_CUDA(
+        cudaFuncSetAttribute(temporal_attn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
   dim3 grid((unsigned)bp, (unsigned)(heads / hpc));
   int threads = (int)(hpc * frames);
@@ -315,8 +318,10 @@ extern "C" int ivv_temporal_attention(const void* qkv, void* o, int64_t clips, i
   if (threads < 64) threads = 64;
   if (frames <= 16)
     temporal_attn_kernel<16><<<grid, threads, smem, stream>>>(in, out, (int)frames, hw, (int)c, heads, hpc, scale);
-  else
+  else if (frames <= 32)
     temporal_attn_kernel<32><<<grid, threads, smem, stream>>>(in, out, (int)frames, hw, (int)c, heads, hpc, scale);
+  else
+    temporal_attn_kernel<64><<<grid, threads, smem, stream>>>(in, out, (int)frames, hw, (int)c, heads, hpc, scale);
   IVV_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -54,6 +54,8 @@ SIGNATURES = {
     "ivv_resize_flow": (c_i32, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_void_p]),
     "ivv_flow_noise_correction": (c_i32, [c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_void_p]),
     "ivv_cfg_ddim_step": (c_i32, [c_void_p, c_void_p, c_void_p, c_i64, c_f32, c_f32, c_f32, c_f32, c_void_p]),
+    "ivv_frames_u8_to_f32": (c_i32, [c_void_p, c_void_p, c_i64, c_i64, c_i32, c_void_p]),
+    "ivv_frames_to_u8": (c_i32, [c_void_p, c_i32, c_void_p, c_i64, c_i64, c_void_p]),
     "ivv_sampler_begin": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64,
                                   c_void_p]),
     "ivv_sampler_partials": (c_i64, [c_i64, c_i64]),
@@ -80,7 +82,7 @@ SIGNATURES = {
     "ivv_convex_upsample": (c_i32, [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
 }
 
-ABI_VERSION = 3  # IVV_ABI_VERSION of include/ivv.h
+ABI_VERSION = 4  # IVV_ABI_VERSION of include/ivv.h
 _lib = None
 LAUNCH_COUNT = 0  # incremented by ops.py for every kernel-launching C-ABI call (bench.py reports it)
 

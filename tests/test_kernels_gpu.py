@@ -293,7 +293,9 @@ def test_cross_attention(clips, frames, s, heads, d):
 
 
 @pytest.mark.parametrize("clips,frames,hw,heads,d", [(3, 16, 96, 8, 40), (2, 16, 24, 8, 160), (1, 5, 35, 8, 80),
-                                                     (1, 32, 6, 8, 160)])
+                                                     (1, 32, 6, 8, 160), (1, 24, 12, 8, 40),
+                                                     # long-form capture of configs[4]: 64 frames per UNet call
+                                                     (1, 64, 10, 8, 40), (2, 48, 6, 8, 80), (1, 64, 4, 8, 160)])
 def test_temporal_attention(clips, frames, hw, heads, d):
     ops = _ops()
     c = heads * d
@@ -496,3 +498,51 @@ def test_conv3x3_splitk(n, ci, co, h, w):
     out2 = ops.conv3x3(_frames(x), ops.pack_conv3x3(wt), n, h, w, bias=b, rowbias=temb, rowbias_group=f * h * w,
                        residual=_frames(res))
     assert torch.equal(out, out2)  # fixed-order reduction: bit-reproducible
+
+
+# ------------------------------------------------------------------------------------------------ frame I/O
+def test_frame_io_matches_the_reference_transform(tmp_path):
+    """video_io: uint8 frames -> [-1, 1] tensors bit-identical to the reference's cv2.cvtColor + ToTensor + Normalize
+    (dataset/loveu_tgve_dataset.py:13-16,50-52); tensors -> uint8 identical to `x / 2 + 0.5`, `* 255`, astype(uint8)
+    (misc_utils/image_utils.py:130,233-235); the file loader against the same pipeline run with cv2 + torchvision."""
+    import cv2
+    import numpy as np
+    from torchvision import transforms
+    from insv2v_b200 import video_io
+    rng = np.random.default_rng(0)
+    frames = rng.integers(0, 256, size=(5, 48, 64, 3), dtype=np.uint8)
+    frames[0, 0, :4] = [[0, 0, 0], [255, 255, 255], [1, 127, 128], [254, 128, 127]]
+    tf = transforms.Compose([transforms.ToTensor(), transforms.Normalize((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))])
+    ref = torch.stack([tf(cv2.cvtColor(f, cv2.COLOR_BGR2RGB)) for f in frames])
+    got = video_io.frames_u8_to_tensor(frames)
+    assert got.shape == (5, 3, 48, 64) and torch.equal(got.cpu(), ref), "uint8 -> [-1,1] is not bit-identical"
+    # way back: the reference's numpy arithmetic
+    x = (torch.rand(4, 3, 40, 56) * 2 - 1)
+    x[0, :, 0, :3] = torch.tensor([[-1.0, 1.0, 0.0]] * 3)
+    want = ((x.numpy().transpose(0, 2, 3, 1) / 2 + 0.5) * 255).astype(np.uint8)
+    u8 = video_io.tensor_to_frames_u8(x.cuda()).cpu().numpy()
+    assert np.array_equal(u8, want), "[-1,1] -> uint8 differs from the reference arithmetic"
+    u8h = video_io.tensor_to_frames_u8(x.half().cuda().unsqueeze(0)).cpu().numpy()
+    assert np.abs(u8h.astype(int) - want.astype(int)).max() <= 1
+    # file round trip: encode a short clip, load it with the product and with the reference's pipeline
+    path = str(tmp_path / "clip.avi")
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 10, (64, 48))
+    if not wr.isOpened():
+        pytest.skip("no video encoder available in this OpenCV build")
+    for f in frames:
+        wr.write(f)
+    wr.release()
+    cap, ref_frames = cv2.VideoCapture(path), []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        ref_frames.append(tf(cv2.cvtColor(cv2.resize(f, (32, 40)), cv2.COLOR_BGR2RGB)))
+    cap.release()
+    got = video_io.load_video_frames(path, (32, 40))
+    assert len(ref_frames) == 5 and torch.equal(got.cpu(), torch.stack(ref_frames))
+    video_io.save_tensor_to_gif(got.unsqueeze(0), str(tmp_path / "out" / "a.gif"), fps=5)
+    video_io.save_tensor_to_images(got.unsqueeze(0), str(tmp_path / "jpg"))
+    from PIL import Image
+    gif = Image.open(str(tmp_path / "out" / "a.gif"))
+    assert gif.n_frames == 5 and gif.size == (32, 40) and len(list((tmp_path / "jpg").iterdir())) == 5

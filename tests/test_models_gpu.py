@@ -252,3 +252,26 @@ def test_full_size_config2_properties():
     ctx2[2] = seeded((77, 768), 5).cuda()
     y3 = m(x, t, encoder_hidden_states=ctx2).sample
     assert torch.equal(y3[0], y1[0]) and not torch.equal(y3[2], y1[2])
+
+
+def test_unet_long_clip_64_frames_vs_oracle():
+    """configs[4] capture form: one UNet call over more than 32 frames (temporal_position_encoding_max_len raised to
+    64, as SURVEY section 8d prescribes for the [3,8,64,48,72] capture). Micro width, 40 and 64 frames, vs the oracle."""
+    from insv2v_b200.unet import UNet3DConditionModel
+    O = _oracle()
+    cfg = dict(O.UNET_CONFIG_MICRO)
+    cfg["motion_module_kwargs"] = dict(cfg["motion_module_kwargs"], temporal_position_encoding_max_len=64)
+    sch = {k: ((1, 64, v[2]) if k.endswith("pos_encoder.pe") else v) for k, v in schema("unet_micro").items()}
+    sd = O.seeded_state_dict(sch, seed=100)
+    m = UNet3DConditionModel(**cfg)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    for frames in (40, 64):
+        x, ctx = seeded((1, 8, frames, 8, 8), 1), seeded((1, 77, cfg["cross_attention_dim"]), 2)
+        t = torch.tensor([300])
+        with torch.no_grad():
+            ref = O.unet3d_forward(sd, cfg, x, t, ctx)
+        y = m(x.cuda(), t.cuda(), encoder_hidden_states=ctx.cuda()).sample
+        _check(f"unet micro, {frames} frames in one call", y, ref)
+    with pytest.raises(ValueError):  # 65 frames exceed the 64-entry positional table (motion_module.py:237-240)
+        m(seeded((1, 8, 65, 8, 8), 1).cuda(), 1, encoder_hidden_states=ctx.cuda())

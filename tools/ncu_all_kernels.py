@@ -1,0 +1,144 @@
+"""Every kernel of the hot path at its config-2 (16 frames, 256x384) shape, one launch each inside a cudaProfilerStart /
+Stop window - the command captured by `ncu --set full --profile-from-start off` (tools/gpu_ncu_all.sh). The first
+entry is EXACTLY the launch bench.py times for `roofline` (conv3x3 320->320 + bias on [48,32,48], no residual)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from insv2v_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda")
+g = torch.Generator(device="cuda").manual_seed(0)
+h16 = lambda *s, scale=1.0: (torch.randn(*s, device=dev, generator=g) * scale).half()  # noqa: E731
+f32 = lambda *s, scale=1.0: torch.randn(*s, device=dev, generator=g) * scale  # noqa: E731
+N, H, W = 48, 32, 48
+calls = []
+
+
+def add(fn):
+    calls.append(fn)
+
+
+def conv(n, ci, co, h, w, res=False, f32out=False):
+    x, wt, b = h16(n * h * w, ci), ops.pack_conv3x3(h16(co, ci, 3, 3, scale=(9 * ci) ** -0.5)), h16(co)
+    r = h16(n * h * w, co) if res else None
+    add(lambda: ops.conv3x3(x, wt, n, h, w, bias=b, residual=r, out_f32=f32out))
+
+
+def lin(rows, k, n, res=True, bias=True):
+    x, w = h16(rows, k), ops.pack_linear(h16(n, k, scale=k ** -0.5))
+    b, r = (h16(n) if bias else None), (h16(rows, n) if res else None)
+    add(lambda: ops.linear(x, w, bias=b, residual=r))
+
+
+def geglu(rows, c):
+    x = h16(rows, c)
+    w, b = ops.pack_geglu(h16(8 * c, c, scale=c ** -0.5), h16(8 * c, scale=0.1))
+    add(lambda: ops.linear(x, w, bias=b, geglu=True))
+
+
+def attn(n, s, skv, d, kv_div=1):
+    c = 8 * d
+    q, kv = h16(n * s, c), h16((n // kv_div) * skv, 2 * c)
+    add(lambda: ops.attention(q, kv[:, :c], kv[:, c:], n_batch=n, s_q=s, s_kv=skv, heads=8, d=d, q_ld=c, kv_ld=2 * c,
+                              kv_div=kv_div))
+
+
+conv(N, 320, 320, 32, 48)                      # the bench's roofline launch (halo kernel, 160-wide)
+conv(N, 640, 640, 16, 24, res=True)            # halo, 8x16 box
+conv(N, 1280, 1280, 8, 12)                     # per-tap pair kernel (box spans frames)
+conv(N, 1280, 1280, 4, 6, res=True)            # split-K + splitk_reduce
+conv(N, 320, 4, 32, 48, f32out=True)           # gemm_tc_kernel (non-persistent, fp32 head)
+conv(16, 128, 128, 256, 384)                   # VAE top level (halo, 128-wide)
+lin(73728, 320, 320)                           # pair160 residual (attention out-projection)
+lin(73728, 320, 960, res=False, bias=False)    # pair160 QKV
+lin(18432, 640, 640)
+lin(4608, 1280, 1280)
+lin(73728, 1280, 320)                          # feed-forward out-projection
+lin(4608, 5120, 1280)                          # v2 pair kernel, 256-wide
+geglu(73728, 320)
+geglu(18432, 640)
+geglu(4608, 1280)
+attn(N, 1536, 1536, 40)
+attn(N, 1536, 77, 40, kv_div=16)
+attn(N, 384, 384, 80)
+attn(N, 384, 77, 80, kv_div=16)
+attn(N, 96, 96, 160)
+attn(N, 24, 24, 160)
+for hw, c in ((1536, 320), (384, 640), (96, 1280), (24, 1280)):
+    qkv = h16(3 * 16 * hw, 3 * c)
+    add(lambda qkv=qkv, hw=hw, c=c: ops.temporal_attention(qkv, 3, 16, hw, c, 8))
+x0, g0, b0 = h16(N * 1536, 320), h16(320), h16(320)
+add(lambda: ops.groupnorm(x0, g0, b0, N, 1536, 32, 16, 1e-5, True))
+add(lambda: ops.groupnorm(x0, g0, b0, N, 1536, 32, 1, 1e-6, False))
+add(lambda: ops.layernorm(x0, g0, b0))
+x2, g2, pe = h16(N * 96, 1280), h16(1280), f32(32, 1280)
+add(lambda: ops.layernorm(x2, g2, g2, pe=pe, rows_per_frame=96, frames=16, pe_start=0))
+wd = ops.pack_conv3x3_im2col(h16(320, 320, 3, 3, scale=0.02))
+add(lambda: ops.conv3x3_s2(x0, wd, N, 32, 48, bias=b0))
+x1 = h16(N * 384, 640)
+add(lambda: ops.upsample_nearest(x1, N, 16, 24))
+add(lambda: ops.concat_channels(x0, x0))
+s5 = f32(3, 8, 16, 32, 48)
+add(lambda: ops.frames_to_ncfhw(ops.ncfhw_to_frames(s5, 8), 3, 8, 16, 32, 48))
+tt = torch.tensor([981.0] * 3, device=dev)
+add(lambda: ops.silu(ops.timestep_embedding(tt, 320)))
+sc = f32(1536, 1536)
+add(lambda: ops.softmax_rows(sc, 512 ** -0.5))
+img, fl, big = f32(4, 4, 32, 48), f32(4, 2, 32, 48, scale=5.0), f32(4, 2, 256, 384, scale=5.0)
+add(lambda: ops.warp_image_f32(img, fl))
+add(lambda: ops.resize_flow_f32(big, 32, 48))
+eps, dl, fll = f32(12, 4, 32, 48), f32(4, 4, 32, 48), f32(12, 4, 2, 32, 48, scale=5.0)
+add(lambda: ops.flow_noise_correction_(eps, dl, fll))
+
+
+def sampler():
+    F_, C, h, w, R, Q = 16, 4, 32, 48, 4, 12
+    hw, n = h * w, F_ * C * h * w
+    table = torch.zeros(4, ops.SAMPLER_ROW, device=dev)
+    table[:, 1], table[:, 2], table[:, 3], table[:, 5], table[:, 7:10] = 0.8, 0.6, 0.9, 0.43, torch.tensor([1.0, 7.5, 1.5], device=dev)
+    state = torch.zeros(4, dtype=torch.int32, device=dev)
+    lat2, cond, eps_cfg = f32(2, n), f32(n), torch.empty(n, device=dev)
+    x, t = torch.empty(3 * F_ * hw, 8, device=dev, dtype=torch.float16), torch.empty(3, device=dev)
+    partials = torch.zeros(ops.sampler_partials(F_, hw), 4, dtype=torch.float64, device=dev)
+    e3, lr, ff = f32(3 * F_ * hw, 4), f32(R * C * hw), f32(Q * R * 2 * hw, scale=3.0)
+
+    def go():
+        ops.sampler_begin(table, state, lat2, cond, x, t, F_, C, hw, 8)
+        ops.sampler_combine(table, state, e3, eps_cfg, partials, F_, C, hw)
+        ops.sampler_update(table, state, lat2, eps_cfg, partials, 2, lr, ff, None, None, None, F_, C, R, Q, h, w)
+        state.zero_()
+    return go
+
+
+add(sampler())
+if os.environ.get("NCU_RAFT", "1") == "1":
+    from insv2v_b200.raft import RAFTFlow
+    rf = RAFTFlow().to(dev)
+    with torch.no_grad():
+        for p in rf.parameters():
+            if p.dim() > 1:
+                p.normal_(0, p[0].numel() ** -0.5)
+    rf.use_cuda_graph = False
+    a, b = torch.rand(4, 3, 256, 384, device=dev), torch.rand(4, 3, 256, 384, device=dev)
+    eng_run = None
+
+    def raft_once():
+        eng = rf._engine
+        if eng is None:
+            rf(a, b)
+            eng = rf._engine
+        return eng.run(a.float().contiguous(), b.float().contiguous(), (256, 384), num_flow_updates=1)
+    add(raft_once)
+
+for fn in calls:  # warm-up (lazy attribute set-up, allocator)
+    fn()
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+for fn in calls:
+    fn()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+print(f"ok: {len(calls)} calls")
