@@ -21,7 +21,7 @@ extern "C" {
 
 typedef void* ivv_stream_t; /* cudaStream_t */
 
-#define IVV_ABI_VERSION 4
+#define IVV_ABI_VERSION 5
 
 int ivv_abi_version(void);
 const char* ivv_last_error(void);
@@ -54,8 +54,22 @@ typedef struct {
   int64_t res_ld;
   int32_t tap_h, tap_w; /* 0, 0: taps = 1 -> 1x1, taps = 9 -> 3x3; otherwise taps must equal tap_h * tap_w (both odd) */
   int32_t relu;         /* 1: D = max(D, 0) after bias / rowbias / residual (not with GEGLU or split-K)           */
-  int32_t reserved_;
+  int32_t rowbias_mod;  /* > 0: rowbias row = (pix / rowbias_group) % rowbias_mod (per-frame tables that repeat per clip) */
+  /* ---- LayerNorm folded into the GEMMs around it (K8; attention.py:241-256, motion_module.py:204-217,236-242) ----
+   * LN(x) W^T = rstd (x W'^T - mean * wsum) + (W beta) with W' = W diag(gamma), wsum[n] = sum_k W'[n][k]: the consumer
+   * GEMM runs on the RAW rows x and applies the per-row statistics in its epilogue; the statistics come from the GEMM
+   * that PRODUCED x, which writes per-row partial (sum, sum of squares) of its fp32 results. Both sides are served by
+   * the short-K pair kernel only: ivv_gemm_ln_fold_ok() tells whether a shape takes it.
+   * row_stats_out: fp32 [rows][n_out / 40][2] or NULL (producer side).
+   * ln_stats: fp32 [rows][ln_parts][2] or NULL (consumer side), ln_wsum: fp16 [n_out]; mean / variance over c columns. */
+  void* row_stats_out;
+  const void* ln_stats;
+  const void* ln_wsum;
+  int32_t ln_parts;
+  float ln_eps;
 } ivv_gemm_args;
+/* 1 if ivv_gemm serves a linear layer [rows, k] -> [rows, n_out] with the kernel that supports row_stats_out / ln_stats */
+int ivv_gemm_ln_fold_ok(int64_t rows, int64_t k, int64_t n_out);
 int ivv_gemm(const ivv_gemm_args* args, ivv_stream_t stream);
 
 /* split-K finish: out[r, c] = sum_z partial[z][r][c] (+bias[c]) (+rowbias[r/group][c]) (+residual[r][c]) -> fp16.   */

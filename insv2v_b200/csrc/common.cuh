@@ -434,7 +434,16 @@ __device__ __forceinline__ void walk_rows(int J, int nf, long long gs, int ss, F
 // a += lo(packed), b += hi(packed): fp32 + fp16 in ONE instruction each (PTX add.f32.f16 -> SASS FHADD with an .H1
 // operand selector), instead of a conversion (HADD2.F32) followed by FADD. Halves the FP instruction count of the GEMM
 // epilogues' bias / residual adds.
+#ifndef IVV_FHADD
+#define IVV_FHADD 1  // -DIVV_FHADD=0: conversion + FADD instead (A/B timing of the FHADD rate, tools/build_variant.sh)
+#endif
 __device__ __forceinline__ void add_h2(float& a, float& b, uint32_t packed) {
+#if !IVV_FHADD
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&packed));
+  a += f.x;
+  b += f.y;
+  return;
+#endif
   asm("{\n\t"
       ".reg .b16 lo, hi;\n\t"
       "mov.b32 {lo, hi}, %2;\n\t"

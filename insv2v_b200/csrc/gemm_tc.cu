@@ -41,6 +41,13 @@ struct GemmKParams {
   long long rowbias_group, rowbias_ld;
   const __half* residual;
   long long res_ld;
+  // pair160 kernel only
+  int rowbias_mod;            // > 0: rowbias row = (pix / rowbias_group) % rowbias_mod
+  float2* row_stats_out;      // [rows][n_out / 40]: per-row partial (sum, sum of squares) of the fp32 results
+  const float2* ln_stats;     // [rows][ln_parts]: statistics of the A rows (LayerNorm folded into this GEMM)
+  const __half* ln_wsum;      // [n_out]
+  int ln_parts;
+  float ln_eps, ln_inv_c;
 };
 
 constexpr int kBlockM = 128;
@@ -880,10 +887,12 @@ constexpr int kP2BiasBytes = 8192;                          // n_out <= 4096
 constexpr int kP2BTileBytes = (kP2BN / 2) * 128;            // 10 KB: this CTA's half of a 160 x 64 weight tile
 constexpr int kP2StageBytes = kABytes + kP2BTileBytes;      // 16 KB activations + 10 KB half weight tile
 constexpr int kP2WsKBlocks = 5;                             // weight-stationary mode: K <= 320
+constexpr int kP2RowStatBytes = 2 * kBlockM * 8;            // folded LayerNorm: (rstd, -mean * rstd) per row, 2 buffers
+constexpr int kP2TileVecBytes = 2 * 3 * kP2BN * 2;          // folded LayerNorm: bias | row bias | wsum slices of the tile
 template <int STAGES, bool WS>
 constexpr int pair160_smem_bytes() {
   return (WS ? STAGES * kABytes + kP2WsKBlocks * kP2BTileBytes : STAGES * kP2StageBytes) + 2 * kP2SlabBytes +
-         kP2BiasBytes + 256;
+         kP2BiasBytes + kP2RowStatBytes + kP2TileVecBytes + 256;
 }
 
 // WS (weight-stationary, K <= 320): these GEMMs are bound by what the SM can pull through TMA (knock-outs in
@@ -905,7 +914,10 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint8_t* b_res = smem + STAGES * kABytes;  // WS only: [k block][80 weight rows x 128 B]
   uint8_t* slabs = smem + kOperandBytes;
   __half* sbias = reinterpret_cast<__half*>(slabs + 2 * kP2SlabBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(slabs + 2 * kP2SlabBytes + kP2BiasBytes);
+  float2* smr = reinterpret_cast<float2*>(slabs + 2 * kP2SlabBytes + kP2BiasBytes);  // [2][128] (rstd, -mean * rstd)
+  __half* tvec = reinterpret_cast<__half*>(slabs + 2 * kP2SlabBytes + kP2BiasBytes + kP2RowStatBytes);  // [2][3][160]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(slabs + 2 * kP2SlabBytes + kP2BiasBytes + kP2RowStatBytes +
+                                                   kP2TileVecBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;  // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
@@ -914,7 +926,8 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint64_t* res_full = slab_free + 2;            // [2] the residual tile has landed in the slab
   uint64_t* b_full = res_full + 2;               // WS: resident weights landed (leader counts both CTAs' bytes)
   uint64_t* b_free = b_full + 1;                 // WS: every MMA that read the resident weights has completed
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_free + 1);
+  uint64_t* stat_full = b_free + 1;              // [2] folded LayerNorm: the row statistics of the tile are in smr
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(stat_full + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -954,6 +967,8 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
     mbar_init(b_full, 1);
     mbar_init(b_free, 1);
+    mbar_init(&stat_full[0], 1);
+    mbar_init(&stat_full[1], 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2sm<2 * kAccStride>(tmem_ptr);
@@ -1093,29 +1108,30 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     }
   } else if (warp == 2) {
-    if (role_elect()) {
-      // ===== store warp: slab -> global (TMA store), then recycle the slab: fetch the residual tile of the tile after
-      // next into it (residual GEMMs) or declare it free =====
-      auto request_res = [&](int u_, int s_) {
-        int ntile_, mg_, w0_, h0_, n0_;
-        decode(u_, ntile_, mg_);
-        origin(mg_, w0_, h0_, n0_);
-        mbar_expect_tx(&res_full[s_], kP2SlabBytes);
-        for (int chunk = 0; chunk < kP2Chunks; ++chunk)
-          tma_load_4d(slabs + s_ * kP2SlabBytes + chunk * kP2ChunkBytes, &tmR, &res_full[s_],
-                      ntile_ * kP2BN + chunk * 32, w0_, h0_, n0_);
-      };
-      if (has_res) {
-        if (u_begin < u_end) request_res(u_begin, 0);
-        if (u_begin + u_step < u_end) request_res(u_begin + u_step, 1);
-      }
-      int local = 0;
-      for (int u = u_begin; u < u_end; u += u_step, ++local) {
-        const int s = local & 1;
+    // ===== store warp: slab -> global (TMA store), then recycle the slab: fetch the residual tile of the tile after
+    // next into it (residual GEMMs) or declare it free =====
+    const bool lead = role_elect();
+    auto request_res = [&](int u_, int s_) {
+      int ntile_, mg_, w0_, h0_, n0_;
+      decode(u_, ntile_, mg_);
+      origin(mg_, w0_, h0_, n0_);
+      mbar_expect_tx(&res_full[s_], kP2SlabBytes);
+      for (int chunk = 0; chunk < kP2Chunks; ++chunk)
+        tma_load_4d(slabs + s_ * kP2SlabBytes + chunk * kP2ChunkBytes, &tmR, &res_full[s_],
+                    ntile_ * kP2BN + chunk * 32, w0_, h0_, n0_);
+    };
+    if (lead && has_res) {
+      if (u_begin < u_end) request_res(u_begin, 0);
+      if (u_begin + u_step < u_end) request_res(u_begin + u_step, 1);
+    }
+    int local = 0;
+    for (int u = u_begin; u < u_end; u += u_step, ++local) {
+      const int s = local & 1;
+      mbar_wait(&slab_full[s], (local >> 1) & 1);
+      if (lead) {
         int ntile, mg, w0, h0, n0;
         decode(u, ntile, mg);
         origin(mg, w0, h0, n0);
-        mbar_wait(&slab_full[s], (local >> 1) & 1);
         stamp(local, 9);
         if (p.dbg_skip != 3) {
           for (int chunk = 0; chunk < kP2Chunks; ++chunk)
@@ -1133,7 +1149,81 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
         stamp(local, 12);
       }
-      bulk_wait_group<0>();
+      __syncwarp();
+    }
+    if (lead) bulk_wait_group<0>();
+  } else if (warp == 3) {
+    // ===== statistics warp (folded LayerNorm only): turns the partial row sums the producer GEMM left in global memory
+    // into (rstd, -mean * rstd) per row of the tile and stages the tile's bias / row-bias / wsum slices, up to two tiles
+    // ahead of the epilogue. (Done by the store warp between its stores and drains this took ~5 000 clk per tile and
+    // paced the kernel: profiles/r02_gemm_lnfold_trace.txt) =====
+    if (p.ln_stats != nullptr) {
+      const bool lead = role_elect();
+      // statistics of the 128 rows of unit u_ -> smr[b_]; the partial sums are added in a fixed order (deterministic)
+      auto prepare_stats = [&](int u_, int b_) {
+        int ntile_, mg_, w0_, h0_, n0_;
+        decode(u_, ntile_, mg_);
+        origin(mg_, w0_, h0_, n0_);
+        // lane l owns rows l, l + 32, l + 64, l + 96. ln_parts is a multiple of 4 (one pair per 40 producer columns,
+        // 160-wide producer tiles): 16-byte loads, sixteen in flight at a time. (A dependent load -> add chain here cost an
+        // L2 round trip per partial and made the consumer GEMM wait for its statistics: 54 -> 116 us on the QKV GEMM.)
+        float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+        const int n4 = p.ln_parts >> 1;
+        const bool tile_ok = n0_ == 0;
+        for (int i0 = 0; i0 < n4; i0 += 4) {
+          float4 t[4][4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const long long row = (long long)w0_ + lane + 32 * j;  // linear layers only: w0 is the row index
+            const float4* src = reinterpret_cast<const float4*>(p.ln_stats + row * p.ln_parts);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              t[j][i] = (tile_ok && row < p.W && i0 + i < n4) ? __ldg(src + i0 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {  // fixed order: deterministic
+              s1[j] += t[j][i].x;
+              s2[j] += t[j][i].y;
+              s1[j] += t[j][i].z;
+              s2[j] += t[j][i].w;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float mean = s1[j] * p.ln_inv_c;
+          const float var = fmaxf(s2[j] * p.ln_inv_c - mean * mean, 0.f);
+          const float rstd = rsqrtf(var + p.ln_eps);
+          smr[b_ * kBlockM + lane + 32 * j] = make_float2(rstd, -mean * rstd);
+        }
+        // bias, per-frame row bias and wsum slices of this tile -> shared memory. (Read straight from global memory in the
+        // epilogue they cost an L2 round trip each - there is next to no L1 beside 225 KB of shared memory - and the
+        // 40-column pass took 3 000-4 700 clk instead of 1 600: profiles/r02_gemm_lnfold_trace.txt)
+        if (lane < kP2BN / 8) {
+          const int col0 = ntile_ * kP2BN + lane * 8;
+          const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+          uint4* dst = reinterpret_cast<uint4*>(tvec + b_ * 3 * kP2BN) + lane;
+          dst[0] = p.bias != nullptr ? __ldg(reinterpret_cast<const uint4*>(p.bias + col0)) : z;
+          uint4 rv = z;
+          if (p.rowbias != nullptr && n0_ == 0) {  // the host guarantees one table row per tile (group % 128 == 0)
+            long long g_ = (long long)w0_ / p.rowbias_group;
+            if (p.rowbias_mod > 0) g_ %= p.rowbias_mod;
+            rv = __ldg(reinterpret_cast<const uint4*>(p.rowbias + g_ * p.rowbias_ld + col0));
+          }
+          dst[kP2BN / 8] = rv;
+          dst[2 * (kP2BN / 8)] = __ldg(reinterpret_cast<const uint4*>(p.ln_wsum + col0));
+        }
+        __syncwarp();
+        if (lead) mbar_arrive(&stat_full[b_]);
+      };
+      int local = 0;
+      for (int u = u_begin; u < u_end; u += u_step, ++local) {
+        const int b = local & 1;
+        // buffer b was last read by the epilogue of unit local - 2, which arrives on slab_full[b] when it is done
+        if (local >= 2) mbar_wait(&slab_full[b], ((local - 2) >> 1) & 1);
+        prepare_stats(u, b);
+      }
     }
   } else if (warp >= 4) {
     // ===== epilogue: warp e = warp - 4; TMEM lane quarter q = warp & 3 (rows 32q .. 32q+31, thread = row), column
@@ -1142,7 +1232,8 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int part = (warp - 4) >> 2;
     const int r = q * 32 + lane;
     const bool has_bias = p.bias != nullptr;
-    if (has_bias) {
+    const bool staged = p.ln_stats != nullptr;  // bias / row bias / wsum slices come from the store warp's per-tile staging
+    if (has_bias && !staged) {
       const int nvec = p.n_out >> 3;
       for (int i = threadIdx.x - 128; i < nvec; i += 512)
         reinterpret_cast<uint4*>(sbias)[i] = __ldg(reinterpret_cast<const uint4*>(p.bias) + i);
@@ -1160,7 +1251,7 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // N tile of the current unit, advanced by increments (no per-tile division on this path)
     int ntile, mg;
     decode(u_begin < u_end ? u_begin : 0, ntile, mg);
-    const int step_n = n_clusters % n_tiles;
+    const int step_n = n_clusters % n_tiles, step_m = n_clusters / n_tiles;
     const uint32_t empty_addr0 = mapa_shared(smem_u32(&tmem_empty_bar[0]), 0);
     const uint32_t empty_addr1 = mapa_shared(smem_u32(&tmem_empty_bar[1]), 0);
     int local = 0;
@@ -1169,11 +1260,15 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const uint32_t ph = (local >> 1) & 1;
       uint8_t* slab = slabs + buf * kP2SlabBytes;
       uint4 bv[5];
-      if (has_bias) {
+      if (has_bias && !staged) {
         const uint4* bsrc = reinterpret_cast<const uint4*>(sbias + ntile * kP2BN + part * 40);
 #pragma unroll
         for (int v = 0; v < 5; ++v) bv[v] = bsrc[v];
       }
+      // first row of this CTA's 128 (linear layers: the row index itself; only the row-indexed options use it)
+      const int cur_ntile = ntile;
+      const long long cur_row0 = (long long)(mg * 2 + crank) * kBlockM;
+      const bool cur_valid = mg * 2 + crank < p.tiles_w;
       if constexpr (WS) {
         if (++mg == groups) {
           mg = 0;
@@ -1181,7 +1276,11 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
       } else {
         ntile += step_n;
-        if (ntile >= n_tiles) ntile -= n_tiles;
+        mg += step_m;
+        if (ntile >= n_tiles) {
+          ntile -= n_tiles;
+          ++mg;
+        }
       }
       const bool etr = tracing && warp == 4 && lane == 0;
       if (etr) stamp(local, 4);
@@ -1199,6 +1298,16 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       if (has_res) mbar_wait(&res_full[buf], ph);   // residual landed (the fetch was issued after the slab's last store drained)
       else mbar_wait(&slab_free[buf], ph ^ 1);      // the slab's previous store has been read out
       if (etr) stamp(local, 7);
+      // folded LayerNorm (this GEMM's A rows are the un-normalised x): per-row (rstd, -mean * rstd) from the store warp
+      float rstd = 1.f, nmr = 0.f;
+      const uint4* tv = reinterpret_cast<const uint4*>(tvec + buf * 3 * kP2BN + part * 40);  // + 20: row bias, + 40: wsum
+      if (staged) {
+        mbar_wait(&stat_full[buf], ph);
+        const float2 mr = smr[buf * kBlockM + r];
+        rstd = mr.x;
+        nmr = mr.y;
+      }
+      float st_s = 0.f, st_q = 0.f;
       if (p.dbg_skip != 5) {  // dbg_skip 5 (tuning): no arithmetic, nothing written
 #pragma unroll
         for (int v = 0; v < 5; ++v) {
@@ -1206,7 +1315,21 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
           for (int j = 0; j < 8; ++j) x[j] = __uint_as_float(v < 4 ? a0[v * 8 + j] : a1[j]);
           uint4* slot = reinterpret_cast<uint4*>(slab + voff[v]);
-          if (has_bias) add_h8(x, bv[v]);
+          if (staged) {
+            // LN(x) W^T = rstd * (x W'^T) + (-mean * rstd) * wsum; the beta term is part of the bias
+            const uint4 wv = tv[2 * (kP2BN / 8) + v];
+            const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 wf = __half22float2(wh[t]);
+              x[2 * t] = fmaf(rstd, x[2 * t], nmr * wf.x);
+              x[2 * t + 1] = fmaf(rstd, x[2 * t + 1], nmr * wf.y);
+            }
+            if (has_bias) add_h8(x, tv[v]);
+            if (p.rowbias != nullptr) add_h8(x, tv[kP2BN / 8 + v]);
+          } else if (has_bias) {
+            add_h8(x, bv[v]);
+          }
           if (has_res) {
             const uint4 rr = *slot;
             add_h8(x, rr);
@@ -1214,6 +1337,13 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           if (p.relu) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) x[j] = fmaxf(x[j], 0.f);
+          }
+          if (p.row_stats_out != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              st_s += x[j];
+              st_q = fmaf(x[j], x[j], st_q);
+            }
           }
           uint32_t pk[4];
 #pragma unroll
@@ -1224,6 +1354,9 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           *slot = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         }
       }
+      // statistics of this row over the thread's 40 columns, for the LayerNorm folded into the next GEMM
+      if (p.row_stats_out != nullptr && cur_valid && cur_row0 + r < p.W)
+        p.row_stats_out[(cur_row0 + r) * (long long)(p.n_out / 40) + cur_ntile * 4 + part] = make_float2(st_s, st_q);
       if (etr) stamp(local, 8);
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store of the store warp
       __syncwarp();
@@ -1391,11 +1524,18 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKPar
 }  // namespace ivv
 
 namespace ivv {
+// shapes the v3 pair kernel (gemm_tc_pair160_kernel) takes: short K, N a multiple of its 160-wide tile, >= 2 row tiles
+static bool pair160_shape_ok(long long rows, long long k_total, long long n_out) {
+  return k_total <= 1280 && (n_out % 160) == 0 && n_out <= 4096 && rows > kBlockM;
+}
+}  // namespace ivv
+
+namespace ivv {
 // Tuning switches of ivv_gemm, read from the environment ONCE per process (getenv is not on the launch path).
 // -1 = unset. IVV_HALO / IVV_DS / IVV_EPI2 / IVV_PAIR: 0 disables; IVV_CLUSTER=2, IVV_FORCE_BN=32|64|128|160|256,
 // IVV_NO_WS=1, IVV_DEBUG_SKIP=1..5 (knock-outs, results are garbage).
 struct GemmEnv {
-  int halo, ds, epi2, pair, cluster, force_bn, no_ws, dbg_skip;
+  int halo, ds, epi2, pair, cluster, force_bn, no_ws, ws, dbg_skip;
 };
 static const GemmEnv& gemm_env() {
   static const GemmEnv e = [] {
@@ -1411,12 +1551,22 @@ static const GemmEnv& gemm_env() {
     g.cluster = geti("IVV_CLUSTER");
     g.force_bn = geti("IVV_FORCE_BN");
     g.no_ws = geti("IVV_NO_WS");
+    g.ws = geti("IVV_WS");
     g.dbg_skip = geti("IVV_DEBUG_SKIP");
     return g;
   }();
   return e;
 }
 }  // namespace ivv
+
+extern "C" int ivv_gemm_ln_fold_ok(int64_t rows, int64_t k, int64_t n_out) {
+  const ivv::GemmEnv& env = ivv::gemm_env();
+  return ivv::pair160_shape_ok(rows, k, n_out) && (k % 8) == 0 && env.epi2 != 0 && env.pair < 0 && env.cluster < 0 &&
+                 env.force_bn < 0
+             ? 1
+             : 0;
+}
+
 
 // tuning / test hook (not in ivv.h): the pixel box ivv_gemm picks for a [n_img, h, w] activation, and whether the halo
 // kernel accepts it (box inside one frame, whole swizzle atoms per box row, (bh + 2) * bw <= 160)
@@ -1545,10 +1695,33 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
                   persistent_ok && m_tiles >= 2 && env.ds != 0 && env.pair != 0 && env.cluster < 0 && env.force_bn < 0;
   // v3 pair kernel (16-warp epilogue + store warp, 160-wide tiles): every short-K GEMM whose N is a multiple of 160 and
   // that needs no per-row bias. IVV_EPI2=0 falls back to the v2 kernels (tuning hook).
-  const bool pair160 = !halo && !a->geglu && a->rowbias == nullptr && (long long)a->c * a->taps <= 1280 &&
-                       (a->n_out % 160) == 0 && a->n_out <= 4096 && persistent_ok && m_tiles >= 2 && a->splits <= 1 &&
+  const bool is_linear = a->taps == 1 && a->h == 1 && a->n_img == 1;
+  // the pair kernel takes a row-bias table only together with a folded LayerNorm (the store warp stages one table row per
+  // tile), so every 128-row tile must lie inside one group
+  const bool rowbias_ok = a->rowbias == nullptr ||
+                          (is_linear && a->ln_stats != nullptr && (a->rowbias_group % kBlockM) == 0 &&
+                           (a->rowbias_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(a->rowbias) & 15) == 0);
+  const bool pair160 = pair160_shape_ok(a->n_img * a->h * a->w, (long long)a->c * a->taps, a->n_out) && !halo &&
+                       !a->geglu && rowbias_ok && persistent_ok && a->splits <= 1 && m_tiles >= 2 &&
                        (a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0) &&
                        env.epi2 != 0 && env.pair < 0 && env.cluster < 0 && env.force_bn < 0;
+  const bool wants_fold = a->row_stats_out != nullptr || a->ln_stats != nullptr || a->rowbias_mod > 0;
+  IVV_REQUIRE(!wants_fold || (pair160 && is_linear),
+              "ivv_gemm: row_stats_out / ln_stats / rowbias_mod need a linear layer served by the short-K pair kernel "
+              "(ivv_gemm_ln_fold_ok(rows, k, n_out)); got rows=%lld k=%lld n_out=%lld taps=%d",
+              (long long)(a->n_img * a->h * a->w), (long long)a->c, (long long)a->n_out, a->taps);
+  if (a->ln_stats != nullptr) {
+    IVV_REQUIRE(a->ln_wsum != nullptr && a->ln_parts > 0 && a->ln_parts <= 64 && a->ln_eps > 0.f &&
+                    (reinterpret_cast<uintptr_t>(a->ln_wsum) & 15) == 0,
+                "ivv_gemm: ln_stats needs ln_wsum (16-byte aligned), 0 < ln_parts <= 64 and ln_eps > 0");
+  }
+  kp.rowbias_mod = a->rowbias_mod;
+  kp.row_stats_out = reinterpret_cast<float2*>(a->row_stats_out);
+  kp.ln_stats = reinterpret_cast<const float2*>(a->ln_stats);
+  kp.ln_wsum = reinterpret_cast<const __half*>(a->ln_wsum);
+  kp.ln_parts = a->ln_parts;
+  kp.ln_eps = a->ln_eps;
+  kp.ln_inv_c = 1.f / (float)a->c;
   if (ds || pair160) bn_sel = 160;
   const int n_tiles = (int)((a->n_out + bn_sel - 1) / bn_sel);
 
@@ -1610,8 +1783,12 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
     if (env.pair >= 0) pair = pair && env.pair != 0;
     if (pair160) {
       kp.ws_stages = 0;
-      // weight-stationary whenever all of K fits beside the rings (K <= 320, linear); IVV_NO_WS=1 disables (tuning hook)
-      if (a->taps == 1 && kp.kblocks <= kP2WsKBlocks && env.no_ws < 0)
+      // Weight-stationary mode (K <= 320, linear): built and measured NEUTRAL on the residual GEMMs (28.7 vs 28.0 us) and
+      // SLOWER on the 960-wide QKV projection (65.8 vs 53.3 us under ncu: the N-major walk re-reads the 47 MB activation
+      // six times with a reuse distance larger than L2 keeps, 129 MB instead of 48 MB of DRAM reads). These kernels are
+      // bound by the latency of a ring revolution (~4 000 clk per 5-stage ring under load), not by operand bytes
+      // (profiles/r02_gemm_pair160_ncu.txt), so it is opt-in: IVV_WS=1.
+      if (a->taps == 1 && kp.kblocks <= kP2WsKBlocks && env.ws == 1)
         return launch_pair160<5, true>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
       return launch_pair160<5, false>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
     }

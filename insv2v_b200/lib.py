@@ -22,7 +22,8 @@ class GemmArgs(ctypes.Structure):
         ("d", c_void_p), ("d_ld", c_i64), ("out_f32", c_i32), ("splits", c_i32),
         ("bias", c_void_p), ("rowbias", c_void_p), ("rowbias_group", c_i64), ("rowbias_ld", c_i64),
         ("residual", c_void_p), ("res_ld", c_i64),
-        ("tap_h", c_i32), ("tap_w", c_i32), ("relu", c_i32), ("reserved_", c_i32),
+        ("tap_h", c_i32), ("tap_w", c_i32), ("relu", c_i32), ("rowbias_mod", c_i32),
+        ("row_stats_out", c_void_p), ("ln_stats", c_void_p), ("ln_wsum", c_void_p), ("ln_parts", c_i32), ("ln_eps", c_f32),
     ]
 
 
@@ -31,6 +32,7 @@ SIGNATURES = {
     "ivv_abi_version": (c_i32, []),
     "ivv_last_error": (ctypes.c_char_p, []),
     "ivv_gemm": (c_i32, [ctypes.POINTER(GemmArgs), c_void_p]),
+    "ivv_gemm_ln_fold_ok": (c_i32, [c_i64, c_i64, c_i64]),
     "ivv_splitk_reduce": (c_i32, [c_void_p, c_i32, c_i64, c_i64, c_i64, c_void_p, c_void_p, c_i64, c_i64, c_void_p,
                                   c_i64, c_void_p, c_i64, c_void_p]),
     "ivv_im2col_s2": (c_i32, [c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i32, c_void_p]),
@@ -82,7 +84,7 @@ SIGNATURES = {
     "ivv_convex_upsample": (c_i32, [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
 }
 
-ABI_VERSION = 4  # IVV_ABI_VERSION of include/ivv.h
+ABI_VERSION = 5  # IVV_ABI_VERSION of include/ivv.h
 _lib = None
 LAUNCH_COUNT = 0  # incremented by ops.py for every kernel-launching C-ABI call (bench.py reports it)
 

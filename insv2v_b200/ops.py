@@ -140,11 +140,36 @@ def _splitk_policy(rows, k_total, n_out):
     return max(1, min(296 // tiles, k_total // 1024, 8))
 
 
+def ln_fold_ok(rows, k, n_out):
+    """True if ivv_gemm serves the linear layer [rows, k] -> [rows, n_out] with the kernel that can emit row statistics
+    (row_stats_out=) and apply a folded LayerNorm (ln=)."""
+    return bool(_lib.load().ivv_gemm_ln_fold_ok(rows, k, n_out))
+
+
+def pack_ln_linear(gamma, beta, w, b=None, pe=None):
+    """LayerNorm folded into the Linear that follows it: LN(x) W^T + b = rstd (x W'^T - mean wsum) + b' with
+    W' = W diag(gamma), wsum[n] = sum_k W'[n][k] (of the fp16-rounded W', which is what the tensor core multiplies),
+    b' = b + W beta. pe [L, k] (temporal positional encoding added AFTER the norm, motion_module.py:236-242,287) becomes
+    a per-frame bias table pe W^T [L, n]. Returns (packed W' fp16 [1, n, k], b' fp16 [n], wsum fp16 [n], table or None)."""
+    wf, g32, b32 = w.detach().float(), gamma.detach().float(), beta.detach().float()
+    wp = (wf * g32[None, :]).to(F16)
+    wsum = wp.float().sum(dim=1).to(F16).contiguous()
+    bias = wf @ b32
+    if b is not None:
+        bias = bias + b.detach().float()
+    table = (pe.detach().float() @ wf.t()).to(F16).contiguous() if pe is not None else None
+    return pack_linear(wp), bias.to(F16).contiguous(), wsum, table
+
+
 def gemm(a, wgt, *, n_img, h, w, c, n_out=None, taps=1, a_ld=None, bias=None, rowbias=None, rowbias_group=0,
-         residual=None, geglu=False, out=None, out_f32=False, _splits=1, tap_hw=None, relu=False):
+         residual=None, geglu=False, out=None, out_f32=False, _splits=1, tap_hw=None, relu=False, rowbias_mod=0,
+         row_stats_out=None, ln=None):
     """D = conv/linear(A, W) with fused epilogue; A rows are pixels [n_img*h*w, a_ld], W packed by pack_*().
     a / out / residual may be column-slice views of wider row-major buffers (their row stride is passed as the
-    leading dimension). tap_hw = (kh, kw): odd stride-1 'same' window other than 1x1 / 3x3 (taps = kh*kw)."""
+    leading dimension). tap_hw = (kh, kw): odd stride-1 'same' window other than 1x1 / 3x3 (taps = kh*kw).
+    row_stats_out: fp32 [rows, n_out // 40, 2] receiving per-row partial (sum, sum of squares) of the results;
+    ln = (stats [rows, parts, 2] fp32, wsum fp16 [n_out], eps): A holds UN-normalised rows whose LayerNorm is applied
+    in the epilogue (weights from pack_ln_linear). Both need ln_fold_ok(rows, c, n_out)."""
     _chk16v(a, "a"), _chk16(wgt, "wgt"), _chk16(bias, "bias"), _chk16(rowbias, "rowbias"), _chk16v(residual, "residual")
     if wgt.dim() != 3 or wgt.shape[0] != taps:
         raise ValueError(f"weight must be [taps={taps}, n_out, k_pad], got {tuple(wgt.shape)}")
@@ -154,6 +179,7 @@ def gemm(a, wgt, *, n_img, h, w, c, n_out=None, taps=1, a_ld=None, bias=None, ro
     cols = n_out // 2 if geglu else n_out
     # split-K for the few-row / long-K convolutions of the 4x6 and 8x12 levels: too few output tiles for 148 SMs
     splits = _splitk_policy(rows, c * taps, n_out) if (SPLITK and not geglu and not out_f32 and not relu and
+                                                        row_stats_out is None and ln is None and
                                                         tap_hw is None and a.is_contiguous() and
                                                         (residual is None or residual.is_contiguous()) and
                                                         (out is None or (out.dtype == F16 and out.is_contiguous()))
@@ -185,21 +211,40 @@ def gemm(a, wgt, *, n_img, h, w, c, n_out=None, taps=1, a_ld=None, bias=None, ro
     args.bias = bias.data_ptr() if bias is not None else None
     if rowbias is not None:
         args.rowbias, args.rowbias_group, args.rowbias_ld = rowbias.data_ptr(), rowbias_group, rowbias.shape[-1]
+        args.rowbias_mod = rowbias_mod
+    if row_stats_out is not None:
+        if (row_stats_out.dtype != torch.float32 or not row_stats_out.is_contiguous()
+                or row_stats_out.numel() != rows * (n_out // 40) * 2):
+            raise ValueError(f"row_stats_out must be contiguous fp32 [rows={rows}, {n_out // 40}, 2]")
+        args.row_stats_out = row_stats_out.data_ptr()
+    if ln is not None:
+        stats, wsum, eps = ln
+        _chk16(wsum, "ln wsum")
+        if stats.dtype != torch.float32 or not stats.is_contiguous() or stats.dim() != 3 or stats.shape[0] != rows \
+                or stats.shape[2] != 2 or wsum.numel() != n_out:
+            raise ValueError(f"ln: stats must be fp32 [rows={rows}, parts, 2] and wsum fp16 [{n_out}]")
+        args.ln_stats, args.ln_wsum, args.ln_parts, args.ln_eps = stats.data_ptr(), wsum.data_ptr(), stats.shape[1], eps
     if residual is not None:
         args.residual, args.res_ld = residual.data_ptr(), residual.stride(-2)
     e0 = Prof.begin()
     _lib.check(_lib.load().ivv_gemm(ctypes.byref(args), _s()), "ivv_gemm")
     if e0 is not None:
         Prof.end(e0, ("gemm", rows, c * taps, n_out, "geglu" if geglu else "", "res" if residual is not None else ""),
-                 2.0 * rows * c * taps * n_out, 2.0 * (rows * c + rows * cols + n_out * c * taps))
+                 2.0 * rows * c * taps * n_out,
+                 2.0 * (rows * c + rows * cols * (2 if residual is not None else 1) + n_out * c * taps))
     _count()
     return out
 
 
-def linear(x, wgt, bias=None, residual=None, geglu=False, out=None):
-    """x [rows, k] -> [rows, n_out] (nn.Linear semantics)."""
+def linear(x, wgt, bias=None, residual=None, geglu=False, out=None, **kw):
+    """x [rows, k] -> [rows, n_out] (nn.Linear semantics); kw: row_stats_out / ln / rowbias* of gemm()."""
     rows, k = x.shape
-    return gemm(x, wgt, n_img=1, h=1, w=rows, c=k, bias=bias, residual=residual, geglu=geglu, out=out)
+    return gemm(x, wgt, n_img=1, h=1, w=rows, c=k, bias=bias, residual=residual, geglu=geglu, out=out, **kw)
+
+
+def row_stats(rows, n_out, device):
+    """Buffer for gemm(row_stats_out=): per row, one (sum, sum of squares) pair per 40 output columns."""
+    return empty((rows, n_out // 40, 2), torch.float32, device)
 
 
 def conv3x3(x, wgt, n_img, h, w, bias=None, rowbias=None, rowbias_group=0, residual=None, out=None, out_f32=False):

@@ -429,6 +429,8 @@ class _Engine:
         self.device = device
         self.cfg = model.config
         self.graphs = {}
+        import os as _os
+        self.fold_ln = _os.environ.get("IVV_LN_FOLD", "1") != "0"  # tuning hook: 0 keeps every LayerNorm a kernel
         m = model
         dev = device
         self.w = {}
@@ -462,6 +464,13 @@ class _Engine:
         def pk_ln(ln):
             return (_h(ln.weight, dev), _h(ln.bias, dev), ln.eps)
 
+        def pk_fold(ln, weight, pe=None):
+            """LayerNorm `ln` folded into the bias-free Linear `weight` that consumes it (ops.pack_ln_linear)."""
+            wp, b, wsum, table = ops.pack_ln_linear(ln.weight.detach().to(dev), ln.bias.detach().to(dev),
+                                                    weight.detach().to(dev), None,
+                                                    None if pe is None else pe.detach()[0].to(dev))
+            return dict(w=wp, b=b, wsum=wsum, eps=ln.eps, pe=table)
+
         def pk_spatial(name, s):
             b = s.transformer_blocks[0]
             W[name] = dict(norm=(_h(s.norm.weight, dev), _h(s.norm.bias, dev)), groups=s.norm.num_groups,
@@ -469,7 +478,11 @@ class _Engine:
                            pin=(ops.pack_linear(s.proj_in.weight.detach().to(dev)), _h(s.proj_in.bias, dev)),
                            pout=(ops.pack_linear(s.proj_out.weight.detach().to(dev)), _h(s.proj_out.bias, dev)),
                            ln1=pk_ln(b.norm1), ln2=pk_ln(b.norm2), ln3=pk_ln(b.norm3),
-                           attn1=pk_attn(b.attn1, True), attn2=pk_attn(b.attn2, False), ff=pk_ff(b.ff))
+                           attn1=pk_attn(b.attn1, True), attn2=pk_attn(b.attn2, False), ff=pk_ff(b.ff),
+                           # norm1 -> fused q|k|v, norm2 -> cross-attention to_q, each folded into its GEMM
+                           f1=pk_fold(b.norm1, torch.cat([b.attn1.to_q.weight, b.attn1.to_k.weight,
+                                                          b.attn1.to_v.weight], 0)),
+                           f2=pk_fold(b.norm2, b.attn2.to_q.weight))
 
         def pk_motion(name, mm):
             t = mm.temporal_transformer
@@ -481,6 +494,8 @@ class _Engine:
                     d["ln"] = pk_ln(ln)
                     d["pe"] = (a.pos_encoder.pe.detach()[0].to(device=dev, dtype=torch.float32).contiguous()
                                if a.pos_encoder is not None else None)
+                    d["fold"] = pk_fold(ln, torch.cat([a.to_q.weight, a.to_k.weight, a.to_v.weight], 0),
+                                        a.pos_encoder.pe if a.pos_encoder is not None else None)
                     attn.append(d)
                 blocks.append(dict(attn=attn, ff_ln=pk_ln(tb.ff_norm), ff=pk_ff(tb.ff)))
             W[name] = dict(norm=(_h(t.norm.weight, dev), _h(t.norm.bias, dev)), eps=t.norm.eps, heads=t.heads,
@@ -570,24 +585,41 @@ class _Engine:
         res = x if p["sc"] is None else ops.linear(x, p["sc"][0], bias=p["sc"][1])
         return ops.conv3x3(hcur, p["c2"][0], n, h, w, bias=p["c2"][1], residual=res)
 
+    def _fold(self, rows, c):
+        """LayerNorm folding (K8) is on when producer (N = c) and consumers (N = c, 3c) take the short-K pair kernel."""
+        return self.fold_ln and ops.ln_fold_ok(rows, c, c) and ops.ln_fold_ok(rows, c, 3 * c)
+
     def _spatial(self, x, name, st):
         p = self.w[name]
         n, h, w, f = st["n"], st["h"], st["w"], st["f"]
         c = x.shape[-1]
         s = h * w
+        rows = n * s
         heads = p["heads"]
         d = c // heads
+        fold = self._fold(rows, c)
         hs = ops.groupnorm(x, *p["norm"], n, s, p["groups"], 1, p["eps"], False)
-        hs = ops.linear(hs, p["pin"][0], bias=p["pin"][1])
-        # self-attention
-        nrm = ops.layernorm(hs, *p["ln1"][:2], eps=p["ln1"][2])
-        qkv = ops.linear(nrm, p["attn1"]["qkv"])
+        # self-attention. Folded form: proj_in also emits the row statistics of its output, and the q|k|v GEMM applies
+        # LayerNorm(norm1) to the raw rows in its epilogue (no LayerNorm kernel, no normalised copy of the activations)
+        st1 = ops.row_stats(rows, c, x.device) if fold else None
+        hs = ops.linear(hs, p["pin"][0], bias=p["pin"][1], row_stats_out=st1)
+        if fold:
+            f1 = p["f1"]
+            qkv = ops.linear(hs, f1["w"], bias=f1["b"], ln=(st1, f1["wsum"], f1["eps"]))
+        else:
+            nrm = ops.layernorm(hs, *p["ln1"][:2], eps=p["ln1"][2])
+            qkv = ops.linear(nrm, p["attn1"]["qkv"])
         ao = ops.attention(_Col(qkv, 0), _Col(qkv, c), _Col(qkv, 2 * c), n_batch=n, s_q=s, s_kv=s, heads=heads, d=d,
                            q_ld=3 * c, kv_ld=3 * c)
-        hs = ops.linear(ao, p["attn1"]["out"][0], bias=p["attn1"]["out"][1], residual=hs)
+        st2 = ops.row_stats(rows, c, x.device) if fold else None
+        hs = ops.linear(ao, p["attn1"]["out"][0], bias=p["attn1"]["out"][1], residual=hs, row_stats_out=st2)
         # cross-attention: K/V once per clip (the reference repeats ctx per frame, attention.py:96)
-        nrm = ops.layernorm(hs, *p["ln2"][:2], eps=p["ln2"][2])
-        q = ops.linear(nrm, p["attn2"]["q"])
+        if fold:
+            f2 = p["f2"]
+            q = ops.linear(hs, f2["w"], bias=f2["b"], ln=(st2, f2["wsum"], f2["eps"]))
+        else:
+            nrm = ops.layernorm(hs, *p["ln2"][:2], eps=p["ln2"][2])
+            q = ops.linear(nrm, p["attn2"]["q"])
         kv = st["ctx_kv"][name]  # projected once per context, not once per denoising step (_context_kv)
         ao = ops.attention(q, _Col(kv, 0), _Col(kv, c), n_batch=n, s_q=s, s_kv=st["ctx_len"], heads=heads, d=d,
                            q_ld=c, kv_ld=2 * c, kv_div=f)
@@ -603,16 +635,34 @@ class _Engine:
         n, h, w, f, b = st["n"], st["h"], st["w"], st["f"], st["b"]
         c = x.shape[-1]
         s = h * w
+        rows = n * s
+        # (with several transformer blocks per module the feed-forward output would have to emit statistics too; its
+        # K = 4c is outside the short-K kernel, so folding is limited to the single-block modules InsV2V uses)
+        # ... and to frames of whole 128-row tiles when there is a positional encoding (one pe row per tile)
+        fold = self._fold(rows, c) and len(p["blocks"]) == 1 and \
+            (s % 128 == 0 or all(a["pe"] is None for a in p["blocks"][0]["attn"]))
         hs = ops.groupnorm(x, *p["norm"], n, s, 32, 1, p["eps"], False)
-        hs = ops.linear(hs, p["pin"][0], bias=p["pin"][1])
+        stats = ops.row_stats(rows, c, x.device) if fold else None
+        hs = ops.linear(hs, p["pin"][0], bias=p["pin"][1], row_stats_out=stats)
         for blk in p["blocks"]:
-            for a in blk["attn"]:
+            n_attn = len(blk["attn"])
+            for i, a in enumerate(blk["attn"]):
                 pe = a["pe"]
-                nrm = ops.layernorm(hs, *a["ln"][:2], eps=a["ln"][2], pe=pe, rows_per_frame=s, frames=f,
-                                    pe_start=st["pe_start"])
-                qkv = ops.linear(nrm, a["qkv"])
+                if fold:
+                    # LayerNorm + positional encoding folded into the q|k|v GEMM: the pe rows become a per-frame bias
+                    # table (pe W^T), indexed by (row / pixels-per-frame) % frames
+                    fd = a["fold"]
+                    kw = {}
+                    if fd["pe"] is not None:
+                        kw = dict(rowbias=fd["pe"][st["pe_start"]:st["pe_start"] + f], rowbias_group=s, rowbias_mod=f)
+                    qkv = ops.linear(hs, fd["w"], bias=fd["b"], ln=(stats, fd["wsum"], fd["eps"]), **kw)
+                else:
+                    nrm = ops.layernorm(hs, *a["ln"][:2], eps=a["ln"][2], pe=pe, rows_per_frame=s, frames=f,
+                                        pe_start=st["pe_start"])
+                    qkv = ops.linear(nrm, a["qkv"])
                 ao = ops.temporal_attention(qkv, b, f, s, c, p["heads"])
-                hs = ops.linear(ao, a["out"][0], bias=a["out"][1], residual=hs)
+                stats = ops.row_stats(rows, c, x.device) if (fold and i + 1 < n_attn) else None
+                hs = ops.linear(ao, a["out"][0], bias=a["out"][1], residual=hs, row_stats_out=stats)
             nrm = ops.layernorm(hs, *blk["ff_ln"][:2], eps=blk["ff_ln"][2])
             g = ops.linear(nrm, blk["ff"]["geglu"][0], bias=blk["ff"]["geglu"][1], geglu=True)
             hs = ops.linear(g, blk["ff"]["out"][0], bias=blk["ff"]["out"][1], residual=hs)

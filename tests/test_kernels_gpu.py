@@ -108,6 +108,51 @@ def test_linear_pair160_variants(rows, k, n, bias, res, relu):
     assert torch.equal(out2, out.contiguous())
 
 
+@pytest.mark.parametrize("rows,c,n,frames,hw", [(4608, 320, 960, 0, 0), (1000, 640, 640, 0, 0), (1152, 1280, 3840, 0, 0),
+                                              (2 * 5 * 384, 320, 960, 5, 384), (3 * 16 * 128, 640, 1920, 16, 128)])
+def test_layernorm_folded_into_gemms(rows, c, n, frames, hw):
+    """K8 fold: the producer GEMM emits per-row partial statistics of its output y, the consumer GEMM computes
+    LayerNorm(y) (+ pe[frame]) W^T from the RAW y (ops.pack_ln_linear). Against fp32 torch; the unfused product path
+    (LayerNorm kernel -> fp16 -> GEMM) is measured beside it and must not be more accurate by more than 10 %."""
+    ops = _ops()
+    assert ops.ln_fold_ok(rows, c, c) and ops.ln_fold_ok(rows, c, n)
+    x0 = h16(rows, c, seed=1)
+    wp = h16(c, c, scale=c ** -0.5, seed=2)
+    bp = h16(c, seed=3)
+    res = h16(rows, c, seed=4) * 2 + 0.75          # non-zero row means: the mean * wsum term matters
+    gamma, beta = (1 + 0.2 * h16(c, seed=5)).float(), 0.3 * h16(c, seed=6).float()
+    w = h16(n, c, scale=c ** -0.5, seed=7)
+    pe = torch.randn(32, c, device="cuda") * 0.5 if frames else None
+    # producer: y = x0 Wp^T + b + res, with row statistics
+    stats = ops.row_stats(rows, c, x0.device)
+    y = ops.linear(x0, ops.pack_linear(wp), bias=bp, residual=res, row_stats_out=stats)
+    y32 = x0.float() @ wp.float().t() + bp.float() + res.float()
+    s_ref = torch.stack([y32.sum(1), (y32 * y32).sum(1)], dim=1)
+    s_got = stats.sum(dim=1)
+    assert torch.allclose(s_got, s_ref, rtol=2e-4, atol=1e-2), (s_got[:2], s_ref[:2])
+    # consumer
+    wfold, bfold, wsum, table = ops.pack_ln_linear(gamma, beta, w, None, pe)
+    kw = {}
+    if frames:
+        kw = dict(rowbias=table[3:3 + frames], rowbias_group=hw, rowbias_mod=frames)
+    out = ops.linear(y, wfold, bias=bfold, ln=(stats, wsum, 1e-5), **kw)
+    # truth: LayerNorm of the fp16 tensor the consumer actually reads, in fp32
+    ln = F.layer_norm(y.float(), (c,), gamma, beta, 1e-5)
+    if frames:
+        fidx = (torch.arange(rows, device="cuda") // hw) % frames
+        ln = ln + pe[3 + fidx]
+    ref = ln @ w.float().t()
+    report(f"LN fold {rows}x{c}->{n}", out, ref, rtol=2e-3, atol=2e-3)
+    # the unfused path of the product on the same inputs
+    g16, b16 = gamma.half(), beta.half()
+    nrm = ops.layernorm(y, g16, b16, eps=1e-5, **(dict(pe=pe, rows_per_frame=hw, frames=frames, pe_start=3) if frames else {}))
+    unf = ops.linear(nrm, ops.pack_linear(w))
+    e_f = (out.float() - ref).norm() / ref.norm()
+    e_u = (unf.float() - ref).norm() / ref.norm()
+    print(f"  rel-L2 vs fp32: folded {e_f:.3e}, LayerNorm kernel + GEMM {e_u:.3e}")
+    assert e_f <= 1.1 * e_u + 1e-5
+
+
 def test_linear_geglu():
     ops = _ops()
     rows, c = 500, 320

@@ -5,7 +5,7 @@ set -e
 name=$1; shift
 cd "$(dirname "$0")/../insv2v_b200"
 mkdir -p build_$name
-for f in api gemm_tc attention_tc norm temporal_attn elementwise warp raft; do
+for f in api gemm_tc attention_tc norm temporal_attn elementwise warp sampler raft; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr "$@" \
        -c csrc/$f.cu -o build_$name/$f.o &
 done

@@ -25,8 +25,19 @@ L.ivv_debug_gemm_trace.restype = None
 buf = torch.zeros(32, 16, dtype=torch.int64, device=dev)
 
 
+LN = os.environ.get("LN", "0") == "1"  # consumer of a folded LayerNorm (+ per-frame rowbias with PE=1)
+extra = {}
+if LN:
+    stats = ops.row_stats(rows, k, dev)
+    ops.linear(torch.randn(rows, k, device=dev).half(), ops.pack_linear(torch.randn(k, k, device=dev) * 0.03),
+               row_stats_out=stats)
+    extra = dict(ln=(stats, torch.randn(n, device=dev).half(), 1e-5))
+    if os.environ.get("PE", "0") == "1":
+        extra.update(rowbias=torch.randn(16, n, device=dev).half(), rowbias_group=1536, rowbias_mod=16)
+
+
 def call(i):
-    ops.gemm(xs[i], w, n_img=1, h=1, w=rows, c=k, bias=bias, residual=rs[i], out=outs[i])
+    ops.gemm(xs[i], w, n_img=1, h=1, w=rows, c=k, bias=bias, residual=rs[i], out=outs[i], **extra)
 
 
 for i in range(nbuf):
@@ -43,7 +54,7 @@ names = ["tma:first", "tma:last", "mma:acc ok", "mma:commit", "epi:top", "epi:dr
 if os.environ.get("IVV_EPI2", "1") != "0" and n % 160 == 0 and k <= 1280:  # v3 pair kernel (gemm_tc_pair160_kernel)
     names = ["tma:first", "tma:last", "mma:acc ok", "mma:commit", "epi:top", "epi:acc", "epi:regs", "epi:slab ok",
              "epi:written", "st:full", "st:issued", "st:drained", "st:res req"]
-print(f"rows={rows} k={k} n={n} res={res}  (SM clocks since the first stamp of CTA 0)")
+print(f"rows={rows} k={k} n={n} res={res} ln={int(LN)}  (SM clocks since the first stamp of CTA 0)")
 print("tile " + " ".join(f"{s:>11s}" for s in names))
 for g in range(32):
     if not (t[g] > 0).any():
