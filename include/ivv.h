@@ -21,7 +21,7 @@ extern "C" {
 
 typedef void* ivv_stream_t; /* cudaStream_t */
 
-#define IVV_ABI_VERSION 5
+#define IVV_ABI_VERSION 6
 
 int ivv_abi_version(void);
 const char* ivv_last_error(void);
@@ -93,6 +93,12 @@ int ivv_groupnorm(const void* x, void* y, const void* gamma, const void* beta, i
                   int32_t groups, int64_t frames_per_group, float eps, int32_t silu, void* stats_ws,
                   size_t stats_ws_bytes, ivv_stream_t stream);
 size_t ivv_groupnorm_ws_bytes(int64_t n_img, int32_t groups, int64_t frames_per_group);
+/* Same over the channel concatenation [x1 | x2] (x1: [n_img, hw, c1], x2: [n_img, hw, c2]) WITHOUT materialising it:
+ * the `torch.cat([hidden_states, res_hidden_states], dim=1)` of the up blocks (unet_blocks.py:561,659) feeding
+ * ResnetBlock3D.norm1 (resnet.py:177). y: fp16 [n_img, hw, c1 + c2].                                                 */
+int ivv_groupnorm2(const void* x1, int64_t c1, const void* x2, int64_t c2, void* y, const void* gamma,
+                   const void* beta, int64_t n_img, int64_t hw, int32_t groups, int64_t frames_per_group, float eps,
+                   int32_t silu, void* stats_ws, size_t stats_ws_bytes, ivv_stream_t stream);
 
 /* ---- K8: LayerNorm (+ temporal positional encoding) ---------------------------------------------------------
  * Replaces nn.LayerNorm at attention.py:168,185,191 / motion_module.py:195,201 and, when pe != NULL, the

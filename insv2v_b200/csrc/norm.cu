@@ -28,8 +28,11 @@ __host__ __device__ inline size_t gn_counter_bytes(long long n_bg) {
   return (size_t)(b < kGnSelfCleanBytes ? kGnSelfCleanBytes : b);
 }
 
-__global__ void gn_stats_kernel(const __half* __restrict__ x, GnWs ws, long long rows_per_bg, int C, int groups,
-                                long long rows_per_cta, int V, int R, float eps) {
+// Two-source form (x2 != nullptr): channels [0, C1) come from x [.., C1], channels [C1, C) from x2 [.., C - C1] - the
+// skip concatenation of the up blocks (unet_blocks.py:561,659) read in place instead of being materialised.
+__global__ void gn_stats_kernel(const __half* __restrict__ x, const __half* __restrict__ x2, int C1, GnWs ws,
+                                long long rows_per_bg, int C, int groups, long long rows_per_cta, int V, int R,
+                                float eps) {
   extern __shared__ __align__(16) float s_part[];  // [R][C][2]
   __shared__ bool s_last;
   griddep_sync();
@@ -44,12 +47,14 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, GnWs ws, long long
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
   if (rsub < R) {
-    const __half* base = x + ((long long)bg * rows_per_bg) * C + vec * 8;
+    const bool second = x2 != nullptr && vec * 8 >= C1;
+    const long long ld = x2 == nullptr ? C : (second ? C - C1 : C1);
+    const __half* base = (second ? x2 + (vec * 8 - C1) : x + vec * 8) + ((long long)bg * rows_per_bg) * ld;
     long long r = row_begin + rsub;
     for (; r + 3LL * R < row_end; r += 4LL * R) {
       uint4 u[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(base + (r + (long long)k * R) * C);
+      for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(base + (r + (long long)k * R) * ld);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const __half2* h = reinterpret_cast<const __half2*>(&u[k]);
@@ -64,7 +69,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, GnWs ws, long long
       }
     }
     for (; r < row_end; r += R) {
-      const uint4 u = *reinterpret_cast<const uint4*>(base + r * C);
+      const uint4 u = *reinterpret_cast<const uint4*>(base + r * ld);
       const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -155,7 +160,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, GnWs ws, long long
 __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y, const __half* __restrict__ gamma,
                                 const __half* __restrict__ beta, const float2* __restrict__ final_,
                                 long long rows_per_bg, int C, int groups, int act, long long rows_per_cta, int V,
-                                int R, const __half* __restrict__ residual) {
+                                int R, const __half* __restrict__ residual, const __half* __restrict__ x2, int C1) {
   griddep_sync();
   const int bg = blockIdx.y;
   const int vec = threadIdx.x % V;
@@ -172,7 +177,9 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict
   }
   const long long row_begin = (long long)blockIdx.x * rows_per_cta;
   const long long row_end = min(rows_per_bg, row_begin + rows_per_cta);
-  const __half* xb = x + ((long long)bg * rows_per_bg) * C + vec * 8;
+  const bool second = x2 != nullptr && vec * 8 >= C1;
+  const long long ld = x2 == nullptr ? C : (second ? C - C1 : C1);
+  const __half* xb = (second ? x2 + (vec * 8 - C1) : x + vec * 8) + ((long long)bg * rows_per_bg) * ld;
   __half* yb = y + ((long long)bg * rows_per_bg) * C + vec * 8;
   // act: 0 none, 1 SiLU, 2 ReLU; residual (channel norm only): y = relu(residual + act(norm(x)))
   const __half* rbase = residual ? residual + ((long long)bg * rows_per_bg) * C + vec * 8 : nullptr;
@@ -207,13 +214,13 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict
   for (; r + 3LL * R < row_end; r += 4LL * R) {
     uint4 u[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(xb + (r + (long long)k * R) * C);
+    for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(xb + (r + (long long)k * R) * ld);
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       *reinterpret_cast<uint4*>(yb + (r + (long long)k * R) * C) = xform(u[k], r + (long long)k * R);
   }
   for (; r < row_end; r += R)
-    *reinterpret_cast<uint4*>(yb + r * C) = xform(*reinterpret_cast<const uint4*>(xb + r * C), r);
+    *reinterpret_cast<uint4*>(yb + r * C) = xform(*reinterpret_cast<const uint4*>(xb + r * ld), r);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -353,7 +360,9 @@ namespace ivv {
 static int groupnorm_impl(const void* x, void* y, const void* gamma, const void* beta, int64_t n_img, int64_t hw,
                           int64_t c, int32_t groups, int64_t frames_per_group, float eps, int32_t act,
                           const void* residual, void* stats_ws, size_t stats_ws_bytes, int max_groups,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, const void* x2 = nullptr, int64_t c1 = 0) {
+  IVV_REQUIRE(x2 == nullptr || (c1 > 0 && c1 < c && c1 % 8 == 0), "ivv_groupnorm2: c1 (%lld) must be a multiple of 8 in (0, c)",
+              (long long)c1);
   IVV_REQUIRE(x && y && stats_ws, "ivv_groupnorm: null pointer");
   IVV_REQUIRE(n_img > 0 && hw > 0 && c > 0, "ivv_groupnorm: empty input");
   IVV_REQUIRE(frames_per_group > 0 && n_img % frames_per_group == 0,
@@ -391,7 +400,8 @@ static int groupnorm_impl(const void* x, void* y, const void* gamma, const void*
     if (smem > 48 * 1024 && configured.first())
       IVV_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     IVV_CHECK_CUDA(launch_pdl(gn_stats_kernel, grid, dim3(threads), smem, stream, reinterpret_cast<const __half*>(x),
-                              ws, rows_per_bg, (int)c, groups, rows_per_cta, V, R, eps));
+                              reinterpret_cast<const __half*>(x2), (int)c1, ws, rows_per_bg, (int)c, groups,
+                              rows_per_cta, V, R, eps));
   }
   {
     long long chunks2 = (148 * 8 + n_bg - 1) / n_bg;
@@ -402,11 +412,20 @@ static int groupnorm_impl(const void* x, void* y, const void* gamma, const void*
     IVV_CHECK_CUDA(launch_pdl(gn_apply_kernel, grid, dim3(threads), 0, stream, reinterpret_cast<const __half*>(x),
                               reinterpret_cast<__half*>(y), reinterpret_cast<const __half*>(gamma),
                               reinterpret_cast<const __half*>(beta), ws.final_, rows_per_bg, (int)c, groups, (int)act,
-                              rpc, V, R, reinterpret_cast<const __half*>(residual)));
+                              rpc, V, R, reinterpret_cast<const __half*>(residual),
+                              reinterpret_cast<const __half*>(x2), (int)c1));
   }
   return 0;
 }
 }  // namespace ivv
+
+extern "C" int ivv_groupnorm2(const void* x1, int64_t c1, const void* x2, int64_t c2, void* y, const void* gamma,
+                              const void* beta, int64_t n_img, int64_t hw, int32_t groups, int64_t frames_per_group,
+                              float eps, int32_t silu, void* stats_ws, size_t stats_ws_bytes, ivv_stream_t stream_) {
+  IVV_REQUIRE(gamma && beta && x2, "ivv_groupnorm2: null pointer");
+  return ivv::groupnorm_impl(x1, y, gamma, beta, n_img, hw, c1 + c2, groups, frames_per_group, eps, silu ? 1 : 0,
+                             nullptr, stats_ws, stats_ws_bytes, 64, reinterpret_cast<cudaStream_t>(stream_), x2, c1);
+}
 
 extern "C" int ivv_groupnorm(const void* x, void* y, const void* gamma, const void* beta, int64_t n_img, int64_t hw,
                              int64_t c, int32_t groups, int64_t frames_per_group, float eps, int32_t silu,

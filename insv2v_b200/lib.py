@@ -39,6 +39,8 @@ SIGNATURES = {
     "ivv_groupnorm": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i32, c_i64, c_f32, c_i32,
                               c_void_p, c_size, c_void_p]),
     "ivv_groupnorm_ws_bytes": (c_size, [c_i64, c_i32, c_i64]),
+    "ivv_groupnorm2": (c_i32, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i32, c_i64,
+                               c_f32, c_i32, c_void_p, c_size, c_void_p]),
     "ivv_layernorm": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_f32, c_void_p, c_i64, c_i64,
                               c_i64, c_void_p]),
     "ivv_attention": (c_i32, [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_i64, c_i64, c_i64,
@@ -84,7 +86,7 @@ SIGNATURES = {
     "ivv_convex_upsample": (c_i32, [c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_void_p]),
 }
 
-ABI_VERSION = 5  # IVV_ABI_VERSION of include/ivv.h
+ABI_VERSION = 6  # IVV_ABI_VERSION of include/ivv.h
 _lib = None
 LAUNCH_COUNT = 0  # incremented by ops.py for every kernel-launching C-ABI call (bench.py reports it)
 

@@ -313,6 +313,24 @@ def groupnorm(x, gamma, beta, n_img, hw, groups, frames_per_group, eps, silu, ou
     return out
 
 
+def groupnorm2(x1, x2, gamma, beta, n_img, hw, groups, frames_per_group, eps, silu, out=None):
+    """GroupNorm(+SiLU) of the channel concatenation [x1 | x2] read in place (no torch.cat / concat kernel)."""
+    _chk16(x1, "x1"), _chk16(x2, "x2"), _chk16(gamma, "gamma"), _chk16(beta, "beta")
+    c1, c2 = x1.shape[-1], x2.shape[-1]
+    if x1.shape[0] != x2.shape[0] or gamma.numel() != c1 + c2:
+        raise ValueError(f"groupnorm2: x1 {tuple(x1.shape)}, x2 {tuple(x2.shape)}, gamma {gamma.numel()}")
+    if out is None:
+        out = empty((x1.shape[0], c1 + c2), F16, x1.device)
+    L = _lib.load()
+    ws = _gn_ws(L.ivv_groupnorm_ws_bytes(n_img, groups, frames_per_group), x1.device)
+    e0 = Prof.begin()
+    _lib.check(L.ivv_groupnorm2(_p(x1), c1, _p(x2), c2, _p(out), _p(gamma), _p(beta), n_img, hw, groups,
+                                frames_per_group, float(eps), int(silu), _p(ws), ws.numel(), _s()), "ivv_groupnorm2")
+    Prof.end(e0, ("groupnorm", n_img * hw, c1 + c2, frames_per_group), 0.0, 6.0 * n_img * hw * (c1 + c2))
+    _lib.LAUNCH_COUNT += 2
+    return out
+
+
 def layernorm(x, gamma, beta, eps=1e-5, pe=None, rows_per_frame=0, frames=0, pe_start=0, out=None):
     _chk16(x, "x"), _chk16(gamma, "gamma"), _chk16(beta, "beta")
     rows, c = x.shape

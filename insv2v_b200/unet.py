@@ -431,6 +431,8 @@ class _Engine:
         self.graphs = {}
         import os as _os
         self.fold_ln = _os.environ.get("IVV_LN_FOLD", "1") != "0"  # tuning hook: 0 keeps every LayerNorm a kernel
+        self.no_concat = _os.environ.get("IVV_NO_CONCAT", "1") != "0"  # tuning hook: 0 materialises the skip concat
+        self._sc_split = {}
         m = model
         dev = device
         self.w = {}
@@ -574,9 +576,23 @@ class _Engine:
                 break
 
     # ---- building blocks (x is frames [n*h*w, c] fp16) -------------------------------------------------------
-    def _resnet(self, x, name, st):
+    def _resnet(self, x, name, st, skip=None):
+        """skip: the skip connection of an up block. The reference concatenates [x | skip] along the channels first
+        (unet_blocks.py:561,659); here norm1 reads both tensors in place and the 1x1 shortcut, linear in its input, is
+        evaluated as W[:, :c1] x + W[:, c1:] skip in two accumulating GEMMs, so the concatenated tensor never exists."""
         p = self.w[name]
         n, h, w, f = st["n"], st["h"], st["w"], st["f"]
+        if skip is not None:
+            c1 = x.shape[-1]
+            hcur = ops.groupnorm2(x, skip, *p["n1"], n, h * w, p["groups"], f, p["eps"], True)
+            temb = st["temb"][:, self.temb_off[name]:]
+            hcur = ops.gemm(hcur, p["c1"][0], n_img=n, h=h, w=w, c=hcur.shape[-1], taps=9, bias=p["c1"][1],
+                            rowbias=_View(temb, self.temb_total), rowbias_group=f * h * w)
+            hcur = ops.groupnorm(hcur, *p["n2"], n, h * w, p["groups"], f, p["eps"], True)
+            wa, wb = self._split_shortcut(name, c1)
+            res = ops.linear(x, wa, bias=p["sc"][1])
+            res = ops.linear(skip, wb, residual=res)
+            return ops.conv3x3(hcur, p["c2"][0], n, h, w, bias=p["c2"][1], residual=res)
         hcur = ops.groupnorm(x, *p["n1"], n, h * w, p["groups"], f, p["eps"], True)
         temb = st["temb"][:, self.temb_off[name]:]  # view: row stride temb_total, used through rowbias_ld
         hcur = ops.gemm(hcur, p["c1"][0], n_img=n, h=h, w=w, c=hcur.shape[-1], taps=9, bias=p["c1"][1],
@@ -584,6 +600,16 @@ class _Engine:
         hcur = ops.groupnorm(hcur, *p["n2"], n, h * w, p["groups"], f, p["eps"], True)
         res = x if p["sc"] is None else ops.linear(x, p["sc"][0], bias=p["sc"][1])
         return ops.conv3x3(hcur, p["c2"][0], n, h, w, bias=p["c2"][1], residual=res)
+
+    def _split_shortcut(self, name, c1):
+        """conv_shortcut weight [1, n, c1 + c2] split at the concatenation boundary (packed once per boundary)."""
+        key = (name, c1)
+        got = self._sc_split.get(key)
+        if got is None:
+            wfull = self.w[name]["sc"][0]  # [1, n, k] fp16, k = c1 + c2 (a multiple of 8: no padding columns)
+            got = (wfull[:, :, :c1].contiguous(), wfull[:, :, c1:].contiguous())
+            self._sc_split[key] = got
+        return got
 
     def _fold(self, rows, c):
         """LayerNorm folding (K8) is on when producer (N = c) and consumers (N = c, 3c) take the short-K pair kernel."""
@@ -696,10 +722,12 @@ class _Engine:
         skips = [(x, h, w)]
         default_up = 2 ** self.num_upsamplers
         forward_size = (h % default_up != 0) or (w % default_up != 0)
+        pending_skip = None
         for step in self.plan:
             kind = step[0]
             if kind == "resnet":
-                x = self._resnet(x, step[1], st)
+                x = self._resnet(x, step[1], st, skip=pending_skip)
+                pending_skip = None
             elif kind == "spatial":
                 x = self._spatial(x, step[1], st)
             elif kind == "motion":
@@ -712,7 +740,10 @@ class _Engine:
             elif kind == "pop_cat":
                 sk, sh, sw = skips.pop()
                 assert (sh, sw) == (st["h"], st["w"]), "skip/feature size mismatch"
-                x = ops.concat_channels(x, sk)
+                if self.no_concat and x.shape[-1] % 8 == 0 and sk.shape[-1] % 8 == 0:
+                    pending_skip = sk  # consumed in place by the resnet that follows (every pop_cat is followed by one)
+                else:
+                    x = ops.concat_channels(x, sk)
             elif kind == "up":
                 wu, bu = W[step[1]]
                 if forward_size:

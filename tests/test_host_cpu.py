@@ -98,7 +98,7 @@ def test_library_exports_every_declared_symbol():
     L = lib.load()
     for name in declared:
         assert hasattr(L, name)
-    assert L.ivv_abi_version() == lib.ABI_VERSION == 5
+    assert L.ivv_abi_version() == lib.ABI_VERSION == 6
     assert L.ivv_groupnorm_ws_bytes(48, 32, 16) >= 3 * 32 * 2 * 8 and L.ivv_groupnorm_ws_bytes(48, 32, 0) == 0
 
 

@@ -258,6 +258,26 @@ def test_groupnorm(b, f, c, h, w, fpg, silu):
     report(f"groupnorm c{c} fpg{fpg}", _nchw(out, b * f, h, w), ref, rtol=1e-3, atol=1e-3)
 
 
+@pytest.mark.parametrize("b,f,c1,c2,h,w,fpg", [(2, 4, 320, 320, 8, 12, 4), (1, 6, 1280, 640, 4, 6, 6), (3, 2, 64, 128, 16, 16, 1),
+                                                (1, 16, 640, 320, 16, 24, 16)])
+def test_groupnorm_two_sources_equals_concat(b, f, c1, c2, h, w, fpg):
+    """ivv_groupnorm2 reads the skip concatenation [x1 | x2] in place (unet_blocks.py:561,659 + resnet.py:177): it must
+    give BIT-identical results to ivv_groupnorm on the materialised concatenation, and match torch."""
+    ops = _ops()
+    x1 = (h16(b * f * h * w, c1, seed=1).float() * 1.5 + 0.3).half()
+    x2 = (h16(b * f * h * w, c2, seed=2).float() * 0.7 - 0.2).half()
+    c = c1 + c2
+    g, be = h16(c, seed=3), h16(c, seed=4)
+    out2 = ops.groupnorm2(x1, x2, g, be, b * f, h * w, 32, fpg, 1e-5, True)
+    cat = ops.concat_channels(x1, x2)
+    assert torch.equal(cat, torch.cat([x1, x2], dim=1))
+    out1 = ops.groupnorm(cat, g, be, b * f, h * w, 32, fpg, 1e-5, True)
+    assert torch.equal(out2, out1), "two-source GroupNorm differs from GroupNorm of the concatenation"
+    x5 = cat.float().reshape(b * f // fpg, fpg, h, w, c).permute(0, 4, 1, 2, 3)
+    ref = F.silu(F.group_norm(x5, 32, g.float(), be.float(), 1e-5)).permute(0, 2, 3, 4, 1).reshape(-1, c)
+    report(f"groupnorm2 {c1}+{c2} fpg{fpg}", out2, ref, rtol=1e-3, atol=1e-3)
+
+
 @pytest.mark.parametrize("rows,c", [(1000, 320), (77, 640), (4608, 1280)])
 def test_layernorm(rows, c):
     ops = _ops()

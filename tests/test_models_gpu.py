@@ -275,3 +275,45 @@ def test_unet_long_clip_64_frames_vs_oracle():
         _check(f"unet micro, {frames} frames in one call", y, ref)
     with pytest.raises(ValueError):  # 65 frames exceed the 64-entry positional table (motion_module.py:237-240)
         m(seeded((1, 8, 65, 8, 8), 1).cuda(), 1, encoder_hidden_states=ctx.cuda())
+
+
+def test_fused_sampler_edge_cases_vs_oracle():
+    """The one-graph-per-step sampler against the pinned oracle loop (oracle.sample_ip2p_video on the oracle UNet) where
+    the reference goldens do not reach: latents whose sides are not multiples of 8 (forward_upsample_size path,
+    unet.py:329-331,409-410), fewer flows than query frames (the reference's zip() truncation, inference.py:374), a
+    captured graph reused with other guidance scales, and the argument checks."""
+    from insv2v_b200.pipeline import InsV2VPipeline
+    O = _oracle()
+    m, cfg, sd = _unet("micro")
+    cd = cfg["cross_attention_dim"]
+    steps = 3
+
+    def unet_fn(x, t, c):
+        return O.unet3d_forward(sd, cfg, x, t, c)
+    lat, cond = seeded((1, 5, 4, 12, 20), 71), seeded((1, 5, 4, 12, 20), 72)
+    tc, tu = seeded((1, 77, cd), 73), seeded((1, 77, cd), 74)
+    lref = seeded((1, 2, 4, 12, 20), 75)
+    flows = [seeded((2, 2, 96, 160), 80 + q, 5.0) for q in range(2)]  # 2 flows for 3 query frames
+    pipe = InsV2VPipeline(m, None, num_ddim_steps=steps)
+    with torch.no_grad():
+        ref1 = O.sample_ip2p_video(unet_fn, lat, tc, tu, cond, 7.5, 1.5, steps)
+        ref2 = O.sample_ip2p_video(unet_fn, lat, tc, tu, cond, 5.0, 1.2, steps, latent_ref=lref, noise_correct_step=1.0,
+                                   flows=flows)
+        ref3 = O.sample_ip2p_video(unet_fn, lat, tc, tu, cond, 3.0, 1.0, steps)
+    g = lambda t: t.cuda()  # noqa: E731
+    out1 = pipe.denoise(g(lat), g(tc), g(tu), g(cond), text_cfg=7.5, img_cfg=1.5)
+    _check("fused sampler, 12x20 latents", out1, ref1, rel=1.2e-2, frac=2.5e-2)
+    out2 = pipe.denoise(g(lat), g(tc), g(tu), g(cond), text_cfg=5.0, img_cfg=1.2, latent_ref=g(lref),
+                        noise_correct_step=1.0, flows=[g(f) for f in flows])
+    _check("fused sampler, 2 flows for 3 query frames", out2, ref2, rel=1.2e-2, frac=2.5e-2)
+    n_graphs = len(pipe._graphs)
+    out3 = pipe.denoise(g(lat), g(tc), g(tu), g(cond), text_cfg=3.0, img_cfg=1.0)   # same shape, other scales
+    assert len(pipe._graphs) == n_graphs, "guidance scales must not need a new graph (they live in the step table)"
+    _check("fused sampler, graph reused with other scales", out3, ref3, rel=1.2e-2, frac=2.5e-2)
+    assert torch.equal(pipe.denoise(g(lat), g(tc), g(tu), g(cond), text_cfg=7.5, img_cfg=1.5), out1)  # deterministic
+    with pytest.raises(ValueError):
+        pipe.denoise(g(lat).repeat(2, 1, 1, 1, 1), g(tc), g(tu), g(cond))
+    with pytest.raises(RuntimeError):
+        pipe.denoise(lat, tc, tu, cond)
+    with pytest.raises(ValueError):
+        pipe.denoise(g(lat), g(tc), g(tu), g(cond), latent_ref=g(lat))  # R must be < F

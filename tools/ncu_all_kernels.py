@@ -114,7 +114,9 @@ def sampler():
 
 
 add(sampler())
-if os.environ.get("NCU_RAFT", "1") == "1":
+if os.environ.get("NCU_RAFT", "1") == "only":
+    calls.clear()
+if os.environ.get("NCU_RAFT", "1") in ("1", "only"):
     from insv2v_b200.raft import RAFTFlow
     rf = RAFTFlow().to(dev)
     with torch.no_grad():

@@ -20,8 +20,8 @@ ix = {h: i for i, h in enumerate(hdr)}
 last = {}
 for r in data:
     name = r[ix["Kernel Name"]].split("(")[0].replace("ivv::", "")
-    if "--by-grid" in sys.argv:  # one row per (kernel, grid size): the same kernel at several shapes
-        name = f"{name} grid={r[ix['launch__grid_size']]}"
+    if "--by-grid" in sys.argv:  # one row per launch: the same kernel at several shapes
+        name = f"{name} #{len(last)} grid={r[ix['launch__grid_size']]}"
     last[name] = r
 w = csv.writer(sys.stdout)
 w.writerow(["Kernel Name"] + [f"{c} [{units[ix[c]]}]" if units[ix[c]] else c for c in COLS if c in ix])
