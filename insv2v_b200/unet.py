@@ -433,6 +433,7 @@ class _Engine:
         self.fold_ln = _os.environ.get("IVV_LN_FOLD", "1") != "0"  # tuning hook: 0 keeps every LayerNorm a kernel
         self.no_concat = _os.environ.get("IVV_NO_CONCAT", "1") != "0"  # tuning hook: 0 materialises the skip concat
         self._sc_split = {}
+        self.nvtx = _os.environ.get("IVV_NVTX", "0") == "1"  # NVTX ranges around the blocks of the plan (profiling)
         m = model
         dev = device
         self.w = {}
@@ -725,6 +726,8 @@ class _Engine:
         pending_skip = None
         for step in self.plan:
             kind = step[0]
+            if self.nvtx:  # IVV_NVTX=1: one range per block of the plan (resnet / spatial / motion / down / up)
+                torch.cuda.nvtx.range_push(" ".join(str(v) for v in step))
             if kind == "resnet":
                 x = self._resnet(x, step[1], st, skip=pending_skip)
                 pending_skip = None
@@ -752,6 +755,8 @@ class _Engine:
                     ho, wo = 2 * st["h"], 2 * st["w"]
                 x, st["h"], st["w"] = ops.upsample_nearest(x, st["n"], st["h"], st["w"], ho, wo)
                 x = ops.conv3x3(x, wu, st["n"], st["h"], st["w"], bias=bu)
+            if self.nvtx:
+                torch.cuda.nvtx.range_pop()
         g, be, eps, groups = W["norm_out"]
         x = ops.groupnorm(x, g, be, st["n"], st["h"] * st["w"], groups, f, eps, True)
         x = ops.conv3x3(x, W["conv_out"][0], st["n"], st["h"], st["w"], bias=W["conv_out"][1], out_f32=True)
