@@ -255,6 +255,19 @@ __device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* m,
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// CTA pairs inside a larger cluster (two pairs sharing an operand): ONE L2 read delivered to the same shared-memory
+// offset of every CTA in cta_mask. The bytes are counted on the barrier at `bar`'s offset in the LEADER (even CTA) of each
+// destination CTA's pair: the peer bit (bit 24) of the issuing CTA's own shared-window address is cleared, as the
+// 2-SM multicast TMA atoms of CUTLASS do. Every mask used here holds CTAs of ONE parity (the issuer's).
+__device__ __forceinline__ void tma_load_4d_2sm_multicast(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                                          int c2, int c3, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+      "h"(cta_mask)
+      : "memory");
+}
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),

@@ -324,11 +324,14 @@ constexpr uint32_t acc_stride_for() {
 // 64 channels -- and the three weight tiles of the filter column it serves (dy = -1, 0, +1).
 constexpr int kHaloRows = 160;
 constexpr int kHaloBytes = kHaloRows * 128;  // 20 KB, a multiple of the 1024-B swizzle atom
+// GEGLU epilogue: hidden | gate bias slices of the tile in shared memory: [2 tiles][2 groups][2 chunks][32 + 32] fp16
+constexpr int kGegluBiasBytes = 2 * 2 * 2 * 64 * 2;
 template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, bool TWO = false, bool HALO = false, bool DS = false>
 constexpr int persist_smem_bytes() {
   // TILEWIDE: the whole fp16 output tile is staged (DS: two such slabs); otherwise one CW-wide slab per epilogue group
   return STAGES * (HALO ? kHaloBytes + 3 * (BN / 2) * 128 : kABytes + (TWO ? BN / 2 : BN) * 128) +
-         (TILEWIDE ? (DS ? 2 : 1) * kBlockM * (GEGLU ? BN / 2 : BN) * 2 : 2 * kBlockM * CW * 2) + 256;
+         (TILEWIDE ? (DS ? 2 : 1) * kBlockM * (GEGLU ? BN / 2 : BN) * 2 : 2 * kBlockM * CW * 2) + 256 +
+         (GEGLU ? kGegluBiasBytes : 0);
 }
 
 template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, int CS, bool TWO, bool HALO = false, bool DS = false>
@@ -354,7 +357,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   // residual tile of tile i+1 can only be requested after the store of tile i has drained it, so every tile pays a full
   // HBM round trip in its epilogue -- with K <= 640 that chain (not the main loop) set the pace. With two, the residual
   // of tile i+1 is requested when the epilogue of tile i STARTS and has a whole tile period to land.
-  static_assert(!DS || (TILEWIDE && !GEGLU), "double staging belongs to the tile-wide residual epilogue");
+  static_assert(!DS || TILEWIDE, "double staging belongs to the tile-wide epilogues");
+  static_assert(!GEGLU || (TILEWIDE && CW == 32 && BN == 256), "GEGLU epilogue: tile-wide staging, 32-column chunks");
   constexpr int kBRows = TWO ? BN / 2 : BN;
   constexpr int kBTileBytes = kBRows * 128;
   constexpr int kAOff = HALO ? kHaloBytes : kABytes;  // offset of the weight tile(s) inside a stage
@@ -602,8 +606,34 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     if constexpr (DS) {
       if (issuer && has_res && my_chunks > 0 && tile_first < total_tiles) request_res(tile_first, 0);
     }
+    // GEGLU: the hidden | gate bias slices of a tile's chunks are staged in shared memory one tile ahead (threads r < 16 of
+    // each group: one 16-byte vector each, requested at the top of the previous tile and written at its end, so the L2
+    // round trip never sits in front of the arithmetic; the eight per-chunk global loads of the old form did).
+    // Layout: [tile parity][group][chunk of the group][hidden 32 | gate 32] fp16.
+    __half* const gb_base = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(full_bar) + 256);
+    auto gbias_fetch = [&](int tile_) -> uint4 {
+      const int ntile_ = tile_ % n_tiles;
+      const int col = ntile_ * BN + ((r >> 2) & 1) * (BN / 2) + (g + 2 * (r >> 3)) * CW + (r & 3) * 8;
+      if (p.bias == nullptr) return make_uint4(0u, 0u, 0u, 0u);
+      if ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) return __ldg(reinterpret_cast<const uint4*>(p.bias + col));
+      union { uint4 u; __half h[8]; } t;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t.h[j] = p.bias[col + j];
+      return t.u;
+    };
+    auto gbias_slot = [&](int buf_) -> uint4* {
+      return reinterpret_cast<uint4*>(gb_base + ((buf_ * 2 + g) * 2 + (r >> 3)) * 64) + (r & 7);
+    };
+    if constexpr (GEGLU) {
+      if (r < 16 && tile_first < total_tiles) *gbias_slot(0) = gbias_fetch(tile_first);  // visible after the tile's top barrier
+    }
     for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++local) {
       uint8_t* const slab = staging + (DS ? (local & 1) * kStagingBytes : 0);
+      uint4 gb_next = make_uint4(0u, 0u, 0u, 0u);
+      const bool gb_pre = GEGLU && r < 16 && tile + tile_step < total_tiles;
+      if constexpr (GEGLU) {
+        if (gb_pre) gb_next = gbias_fetch(tile + tile_step);
+      }
       const int ntile = tile % n_tiles;
       const int mtile = (tile / n_tiles) * CS + crank;
       const int tw = mtile % p.tiles_w;
@@ -626,7 +656,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             // residual GEMM: this tile's slab was refilled by the residual fetch, which already waited for its store;
             // the drain of the PREVIOUS tile's store (it sits behind the producer's loads in the TMA queue: ~1 100 clk
             // in the trace) is waited for after the first chunk, where it has long finished
-            if (!has_res) bulk_wait_group_read<0>();
+            // (GEGLU, two slabs and no residual: only the store issued two tiles ago must have left this slab)
+            if constexpr (GEGLU) bulk_wait_group_read<1>();
+            else if (!has_res) bulk_wait_group_read<0>();
           } else {
             bulk_wait_group_read<0>();
             if (has_res && my_chunks > 0) {
@@ -745,16 +777,23 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             tmem_ld32(taddr + c0 + s, hacc);
             tmem_ld32(taddr + HALF + c0 + s, gacc);
             tmem_ld_wait();
-            const int bcol = ntile * BN + c0 + s;  // interleaved bias order: [128 hidden | 128 gate] per tile
+            // interleaved bias order: [128 hidden | 128 gate] per tile; this chunk's slices were staged by gbias_fetch
+            const uint4* bsm = reinterpret_cast<const uint4*>(gb_base + ((buf * 2 + g) * 2 + ((chunk - g) >> 1)) * 64);
 #pragma unroll
             for (int j8 = 0; j8 < 32; j8 += 8) {
               float hb[8], gb[8];
-              if (p.bias) {
-                load8h(p.bias + bcol + j8, 8, true, hb);
-                load8h(p.bias + bcol + HALF + j8, 8, true, gb);
-              } else {
+              {
+                const uint4 hv4 = bsm[j8 >> 3], gv4 = bsm[4 + (j8 >> 3)];  // same address in every lane: broadcast
+                const __half2* hh = reinterpret_cast<const __half2*>(&hv4);
+                const __half2* gh = reinterpret_cast<const __half2*>(&gv4);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) hb[j] = gb[j] = 0.f;
+                for (int t = 0; t < 4; ++t) {
+                  const float2 hf = __half22float2(hh[t]), gf = __half22float2(gh[t]);
+                  hb[2 * t] = hf.x;
+                  hb[2 * t + 1] = hf.y;
+                  gb[2 * t] = gf.x;
+                  gb[2 * t + 1] = gf.y;
+                }
               }
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -840,6 +879,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         }
         if (etr) stamp(local, 10);
       }
+      if constexpr (GEGLU) {
+        // the other parity's slices were last read in the previous tile, which every thread of the group left before this
+        // thread passed this tile's top barrier; the next tile's top barrier publishes the write
+        if (gb_pre) *gbias_slot((local + 1) & 1) = gb_next;
+      }
       if (NCHUNK == 1 && g == 1) {  // this group had no chunk: still release the accumulator
         tc_fence_before();
         if (lane == 0) release_acc(buf);
@@ -901,15 +945,30 @@ constexpr int pair160_smem_bytes() {
 // in shared memory and only activations stream: 82 KB instead of 133 KB of operands per tile. To keep one N tile per
 // cluster for as long as possible, the (N tile, M pair) units are walked N-major and each cluster takes a contiguous
 // range; the weights are reloaded only where a range crosses into the next N tile.
-template <int STAGES, bool WS>
+//
+// CL = 4 (two pairs per cluster, A multicast): every GEMM of this family that does not sit on the DRAM floor sits on the
+// L2 -> SM throughput cap instead (~6 300 B/clk for the whole chip = ~43 B/clk per SM; ncu: lts__throughput 38-43 % on
+// all of them, 601 MB of L2 traffic in 96 400 clk on the 73728x320->960 QKV projection, of which only 189 MB are
+// algorithmic): a 256x160 pair tile re-reads its activation rows once per N tile. Here the two pairs of a 4-CTA cluster
+// take the SAME 256 rows and two ADJACENT N tiles; each CTA fetches half of the 128-row activation box it shares with
+// its counterpart in the other pair and TMA-multicasts it to both, so the activation bytes leaving L2 halve
+// (operand bytes per cluster and K block: 2 x (32 + 20) KB -> 32 + 40 KB). A stage may be refilled when the MMAs of BOTH
+// pairs have read it (empty barrier count 2, commits multicast to all four CTAs). Linear layers with an even number of
+// N tiles only; 4-CTA clusters fit 132 of the 148 SMs (33 clusters: ivv_debug_cl4_clusters()).
+// RESULT (B200, profiles/r02_linear_ab_cl4_geglu.txt): correct, and 8-15 % SLOWER on every shape it applies to
+// (QKV 73728x320->960 59.3 -> 65.1 us, 18432x640->1920 50.9 -> 56.2, 4608x1280->3840 43.9 -> 50.7): 24 % fewer bytes
+// out of L2 buy nothing, the time follows the number of SMs at work (132 / 148). So the L2 -> SM throughput is NOT what
+// bounds these GEMMs; what a CTA pair can keep in flight is (the ring-latency law). Opt-in.
+template <int STAGES, bool WS, int CL = 2>
 __global__ void __launch_bounds__(kP2Threads, 1)
 gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
                        const __grid_constant__ GemmKParams p, int n_tiles, int total_tiles) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
+  static_assert(CL == 2 || (CL == 4 && !WS), "cluster of one pair, or of two pairs sharing the activation rows");
+  constexpr bool C4 = CL == 4;
   constexpr uint32_t kAccStride = 256;  // TMEM columns per accumulator buffer
-  constexpr uint16_t kMask = 3;
   constexpr int kOperandBytes = WS ? STAGES * kABytes + kP2WsKBlocks * kP2BTileBytes : STAGES * kP2StageBytes;
   uint8_t* b_res = smem + STAGES * kABytes;  // WS only: [k block][80 weight rows x 128 B]
   uint8_t* slabs = smem + kOperandBytes;
@@ -931,14 +990,20 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int crank = (int)cluster_ctarank();
+  const int cl_rank = (int)cluster_ctarank();
+  const int crank = C4 ? (cl_rank & 1) : cl_rank;                    // rank inside the MMA pair (0 = leader)
+  const int pair_id = C4 ? (cl_rank >> 1) : 0;                       // CL = 4: which of the cluster's two pairs
+  const uint32_t lead_rank = C4 ? (uint32_t)(cl_rank & ~1) : 0u;     // cluster rank of this pair's leader
+  const uint16_t kMask = C4 ? (uint16_t)(3u << (2 * pair_id)) : (uint16_t)3;  // the two CTAs of this pair
+  const uint16_t kAllMask = C4 ? (uint16_t)0xF : kMask;              // every CTA that fills stages this pair reads
   const int n_clusters = (int)num_clusters_x();
   const int cid = (int)cluster_id_x();
   const int groups = total_tiles / n_tiles;  // M-tile pairs
-  // units of this cluster: WS -> contiguous range of the N-major order; else round robin over the M-major order
-  const int u_begin = WS ? (int)((long long)cid * total_tiles / n_clusters) : cid;
+  // units of this pair: WS -> contiguous range of the N-major order; else round robin over the M-major order (CL = 4:
+  // the cluster takes units 2s and 2s + 1 -- same rows, adjacent N tiles, n_tiles is even -- one per pair)
+  const int u_begin = WS ? (int)((long long)cid * total_tiles / n_clusters) : C4 ? 2 * cid + pair_id : cid;
   const int u_end = WS ? (int)((long long)(cid + 1) * total_tiles / n_clusters) : total_tiles;
-  const int u_step = WS ? 1 : n_clusters;
+  const int u_step = WS ? 1 : C4 ? 2 * n_clusters : n_clusters;
   const int its_per_tile = p.taps * p.kblocks;
   const bool has_res = p.residual != nullptr && p.dbg_skip != 4;  // dbg_skip 4 (tuning): residual term dropped
   // tuning trace (tools/gemm_trace.py): CTA 0, per tile: 0-1 producer (first / last load issued), 2-3 MMA thread
@@ -956,7 +1021,7 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     tma_prefetch_desc(&tmR);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);   // the leader expects the bytes of both CTAs
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], C4 ? 2 : 1);  // CL = 4: the MMAs of both pairs read (part of) what this CTA loads
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
@@ -1023,7 +1088,7 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               mbar_wait(b_free, bfree_par);
               bfree_par ^= 1;
             }
-            const uint32_t lead_b = mapa_shared(smem_u32(b_full), 0);
+            const uint32_t lead_b = mapa_shared(smem_u32(b_full), lead_rank);
             if (crank == 0) mbar_expect_tx(b_full, 2 * its_per_tile * kP2BTileBytes);
             for (int it = 0; it < its_per_tile; ++it)
               tma_load_3d_2sm(b_res + it * kP2BTileBytes, &tmB, lead_b, it * kBlockK, ntile * kP2BN + crank * (kP2BN / 2), 0);
@@ -1040,14 +1105,21 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             dx = tap % p.tap_w - (p.tap_w >> 1);
           }
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
+          const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), lead_rank);
           if constexpr (WS) {
             if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * kABytes);
             tma_load_4d_2sm(smem + stage * kABytes, &tmA, lead_bar, kb * kBlockK, w0 + dx, h0 + dy, n0);
           } else {
             uint8_t* sa = smem + stage * kP2StageBytes;
             if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * kP2StageBytes);
-            tma_load_4d_2sm(sa, &tmA, lead_bar, kb * kBlockK, w0 + dx, h0 + dy, n0);
+            if constexpr (C4) {
+              // linear layers only (w0 = row index): tmA's box is HALF the 128 rows; this CTA's half goes to itself and
+              // to the CTA of the same pair rank in the other pair, whose own half arrives the same way
+              tma_load_4d_2sm_multicast(sa + pair_id * (kABytes / 2), &tmA, &full_bar[stage], kb * kBlockK,
+                                        w0 + pair_id * (kBlockM / 2), h0, n0, (uint16_t)(5u << crank));
+            } else {
+              tma_load_4d_2sm(sa, &tmA, lead_bar, kb * kBlockK, w0 + dx, h0 + dy, n0);
+            }
             tma_load_3d_2sm(sa + kABytes, &tmB, lead_bar, kb * kBlockK, ntile * kP2BN + crank * (kP2BN / 2), tap);
           }
           if (++stage == STAGES) {
@@ -1092,7 +1164,7 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             if (p.dbg_skip == 1 && (it | k) != 0) continue;  // tuning only: one MMA per tile
             umma_f16_ss_2sm(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
           }
-          umma_commit_2sm(&empty_bar[stage], kMask);
+          umma_commit_2sm(&empty_bar[stage], kAllMask);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -1251,9 +1323,9 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // N tile of the current unit, advanced by increments (no per-tile division on this path)
     int ntile, mg;
     decode(u_begin < u_end ? u_begin : 0, ntile, mg);
-    const int step_n = n_clusters % n_tiles, step_m = n_clusters / n_tiles;
-    const uint32_t empty_addr0 = mapa_shared(smem_u32(&tmem_empty_bar[0]), 0);
-    const uint32_t empty_addr1 = mapa_shared(smem_u32(&tmem_empty_bar[1]), 0);
+    const int step_n = u_step % n_tiles, step_m = u_step / n_tiles;
+    const uint32_t empty_addr0 = mapa_shared(smem_u32(&tmem_empty_bar[0]), lead_rank);
+    const uint32_t empty_addr1 = mapa_shared(smem_u32(&tmem_empty_bar[1]), lead_rank);
     int local = 0;
     for (int u = u_begin; u < u_end; u += u_step, ++local) {
       const int buf = local & 1;
@@ -1498,6 +1570,70 @@ static int launch_pair160(const CUtensorMap& tmA, const CUtensorMap& tmB2, const
   return 0;
 }
 
+// 4-CTA clusters (two pairs, activation rows multicast): how many fit on this device at once (4-CTA clusters leave some
+// SMs of a GPC unused: 33 clusters = 132 of 148 SMs is what the B200 places). Asked once per device; 0 = unavailable.
+template <int STAGES>
+static int pair160_cl4_clusters() {
+  static int cached[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (cached[dev] != 0) return cached[dev] > 0 ? cached[dev] : 0;
+  constexpr int smem = pair160_smem_bytes<STAGES, false>();
+  auto kern = gemm_tc_pair160_kernel<STAGES, false, 4>;
+  int n = 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(4 * (sm_count() / 4)));
+    cfg.blockDim = dim3(kP2Threads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) n = 0;
+  }
+  (void)cudaGetLastError();
+  cached[dev] = n > 0 ? n : -1;
+  return n > 0 ? n : 0;
+}
+
+// tmA here has a HALF box (64 rows): see the CL = 4 note at the kernel
+template <int STAGES>
+static int launch_pair160_cl4(const CUtensorMap& tmA, const CUtensorMap& tmB2, const CUtensorMap& tmD,
+                              const CUtensorMap& tmR, const GemmKParams& kp, int m_tiles, int n_tiles, int max_clusters,
+                              cudaStream_t stream) {
+  constexpr int smem = pair160_smem_bytes<STAGES, false>();
+  auto kern = gemm_tc_pair160_kernel<STAGES, false, 4>;
+  const int groups = (m_tiles + 1) / 2;
+  const int total = groups * n_tiles;  // even: n_tiles is
+  int clusters = max_clusters;
+  if (clusters > total / 2) clusters = total / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(clusters * 4));
+  cfg.blockDim = dim3(kP2Threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  attr[na].id = cudaLaunchAttributeClusterDimension;
+  attr[na].val.clusterDim.x = 4;
+  attr[na].val.clusterDim.y = 1;
+  attr[na].val.clusterDim.z = 1;
+  ++na;
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  IVV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB2, tmD, tmR, kp, n_tiles, total));
+  return 0;
+}
+
 // cluster size 2 (weight tile multicast) whenever the M tiles pair up; IVV_CLUSTER=1 disables it (tuning hook)
 template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE>
 static int launch_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB2, const CUtensorMap& tmB1,
@@ -1525,6 +1661,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmKPar
 
 namespace ivv {
 // shapes the v3 pair kernel (gemm_tc_pair160_kernel) takes: short K, N a multiple of its 160-wide tile, >= 2 row tiles
+constexpr int kCl4MinTiles = 148;  // below one wave of pair tiles nothing is throughput-bound
 static bool pair160_shape_ok(long long rows, long long k_total, long long n_out) {
   return k_total <= 1280 && (n_out % 160) == 0 && n_out <= 4096 && rows > kBlockM;
 }
@@ -1535,7 +1672,7 @@ namespace ivv {
 // -1 = unset. IVV_HALO / IVV_DS / IVV_EPI2 / IVV_PAIR: 0 disables; IVV_CLUSTER=2, IVV_FORCE_BN=32|64|128|160|256,
 // IVV_NO_WS=1, IVV_DEBUG_SKIP=1..5 (knock-outs, results are garbage).
 struct GemmEnv {
-  int halo, ds, epi2, pair, cluster, force_bn, no_ws, ws, dbg_skip;
+  int halo, ds, epi2, pair, cluster, force_bn, no_ws, ws, dbg_skip, geglu_ds, cl4, cl4_min;
 };
 static const GemmEnv& gemm_env() {
   static const GemmEnv e = [] {
@@ -1553,6 +1690,9 @@ static const GemmEnv& gemm_env() {
     g.no_ws = geti("IVV_NO_WS");
     g.ws = geti("IVV_WS");
     g.dbg_skip = geti("IVV_DEBUG_SKIP");
+    g.geglu_ds = geti("IVV_GEGLU_DS");
+    g.cl4 = geti("IVV_CL4");
+    g.cl4_min = geti("IVV_CL4_MIN");
     return g;
   }();
   return e;
@@ -1579,6 +1719,9 @@ extern "C" int ivv_debug_conv_box(int64_t w, int64_t h, int64_t n_img, int32_t w
   *bn = c;
   return ivv::halo_box_ok(a, b, c) ? 1 : 0;
 }
+
+// tuning hook: how many 4-CTA clusters of the short-K pair kernel the current device runs at once (0 = unavailable)
+extern "C" int ivv_debug_cl4_clusters() { return ivv::pair160_cl4_clusters<5>(); }
 
 static long long* g_gemm_trace = nullptr;
 // tuning only: clock64 trace of CTA 0 of the next persistent-kernel launches into buf ([32 tiles][16] int64); NULL = off
@@ -1783,6 +1926,22 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
     if (env.pair >= 0) pair = pair && env.pair != 0;
     if (pair160) {
       kp.ws_stages = 0;
+      // two pairs per cluster sharing their activation rows (see the CL = 4 note at the kernel): linear layers with an
+      // even number of N tiles and at least cl4_min 256x160 tiles. Measured SLOWER (profiles/r02_linear_ab_cl4_geglu.txt):
+      // opt-in with IVV_CL4=1, IVV_CL4_MIN=<tiles> moves the bar.
+      if (is_linear && (n_tiles % 2) == 0 && kp.bw == kBlockM && env.cl4 == 1 &&
+          (long long)((m_tiles + 1) / 2) * n_tiles >= (env.cl4_min >= 0 ? env.cl4_min : kCl4MinTiles)) {
+        const int max_clusters = pair160_cl4_clusters<5>();
+        if (max_clusters >= 8) {
+          CUtensorMap tmAh;
+          const uint64_t dims[4] = {(uint64_t)a->c, (uint64_t)a->w, (uint64_t)a->h, (uint64_t)a->n_img};
+          const uint64_t strides[4] = {2, (uint64_t)a->a_ld * 2, (uint64_t)a->a_ld * 2 * a->w,
+                                       (uint64_t)a->a_ld * 2 * a->w * a->h};
+          const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)(kBlockM / 2), 1u, 1u};
+          if (int rc = make_tmap_f16(&tmAh, a->a, 4, dims, strides, box, 128)) return rc;
+          return launch_pair160_cl4<5>(tmAh, tmB2, tmD, tmR, kp, m_tiles, n_tiles, max_clusters, stream);
+        }
+      }
       // Weight-stationary mode (K <= 320, linear): built and measured NEUTRAL on the residual GEMMs (28.7 vs 28.0 us) and
       // SLOWER on the 960-wide QKV projection (65.8 vs 53.3 us under ncu: the N-major walk re-reads the 47 MB activation
       // six times with a reuse distance larger than L2 keeps, 129 MB instead of 48 MB of DRAM reads). These kernels are
@@ -1812,7 +1971,14 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
     if (pair && cs == 1) {
 #define IVV_PAIR_LAUNCH(BN_, ST_, CW_, GG_, TW_) \
   return launch_persistent_cs<BN_, ST_, CW_, GG_, TW_, 2, true>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream)
-      if (a->geglu) IVV_PAIR_LAUNCH(256, 6, 32, true, true);
+      if (a->geglu) {
+        // short main loops (K <= 320: the 32x48 level): the epilogue sets the pace, so spend one pipeline stage on a second
+        // output slab -- the store of tile i drains while tile i+1 is written. IVV_GEGLU_DS=0 disables, =2 takes it for
+        // every K (tuning hooks).
+        if (env.geglu_ds != 0 && (kp.taps * kp.kblocks <= 5 || env.geglu_ds == 2))
+          return launch_persistent_cs<256, 5, 32, true, true, 2, true, false, true>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
+        IVV_PAIR_LAUNCH(256, 6, 32, true, true);
+      }
       switch (bn_sel) {
         case 256:
           if (k_total >= 2560) IVV_PAIR_LAUNCH(256, 6, 64, false, false);

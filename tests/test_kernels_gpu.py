@@ -153,19 +153,25 @@ def test_layernorm_folded_into_gemms(rows, c, n, frames, hw):
     assert e_f <= 1.1 * e_u + 1e-5
 
 
-def test_linear_geglu():
+@pytest.mark.parametrize("rows,c,mult,bias", [(500, 320, 8, True), (40000, 320, 8, True), (40000, 320, 8, False),
+                                              (9100, 640, 8, True), (2400, 1280, 4, True)])
+def test_linear_geglu(rows, c, mult, bias):
+    """GEGLU epilogue (hidden * gelu(gate), tile-interleaved weights). The larger cases give every cluster a run of
+    tiles: the bias slices staged one tile ahead in shared memory and the two alternating output slabs (K <= 320) are
+    only exercised across tile boundaries."""
     ops = _ops()
-    rows, c = 500, 320
     x = h16(rows, c, seed=1)
-    w = h16(8 * c, c, scale=c ** -0.5, seed=2)
-    b = h16(8 * c, scale=0.1, seed=3)
-    wp, bp = ops.pack_geglu(w, b)
-    out = ops.linear(x, wp, bias=bp, geglu=True)
-    y = x.float() @ w.float().t() + b.float()
+    w = h16(mult * c, c, scale=c ** -0.5, seed=2)
+    b = h16(mult * c, scale=0.5, seed=3) if bias else None
+    wp, bp = ops.pack_geglu(w, b if bias else torch.zeros(mult * c, device="cuda", dtype=torch.float16))
+    out = ops.linear(x, wp, bias=bp if bias else None, geglu=True)
+    y = x.float() @ w.float().t()
+    if bias:
+        y = y + b.float()
     hid, gate = y.chunk(2, dim=-1)
     ref = hid * F.gelu(gate)
-    assert out.shape == (rows, 4 * c)
-    report("geglu", out, ref)
+    assert out.shape == (rows, mult * c // 2)
+    report(f"geglu {rows}x{c}->{mult * c // 2} bias={bias}", out, ref)
 
 
 def test_linear_out_f32_and_rowbias():
