@@ -93,6 +93,9 @@ int ivv_groupnorm(const void* x, void* y, const void* gamma, const void* beta, i
                   int32_t groups, int64_t frames_per_group, float eps, int32_t silu, void* stats_ws,
                   size_t stats_ws_bytes, ivv_stream_t stream);
 size_t ivv_groupnorm_ws_bytes(int64_t n_img, int32_t groups, int64_t frames_per_group);
+/* 1 when ivv_groupnorm / ivv_groupnorm2 on this shape run as ONE kernel (the whole tensor held in shared memory between
+ * statistics and normalisation, one CTA per SM), 0 for the statistics + apply pair: launch accounting of the caller. */
+int ivv_groupnorm_is_fused(int64_t n_img, int64_t hw, int64_t c, int32_t groups, int64_t frames_per_group);
 /* Same over the channel concatenation [x1 | x2] (x1: [n_img, hw, c1], x2: [n_img, hw, c2]) WITHOUT materialising it:
  * the `torch.cat([hidden_states, res_hidden_states], dim=1)` of the up blocks (unet_blocks.py:561,659) feeding
  * ResnetBlock3D.norm1 (resnet.py:177). y: fp16 [n_img, hw, c1 + c2].                                                 */

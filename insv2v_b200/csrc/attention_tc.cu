@@ -73,7 +73,10 @@ template <int DC, int NS, bool PAIR = false, int POLY = 0>
 __device__ __forceinline__ void softmax_tile(const AttnParams& p, int r, uint32_t lane_off, uint32_t tmem_S,
                                              uint32_t tmem_O, uint8_t* sP, uint8_t* sV, uint64_t* s_full,
                                              uint64_t* p_full, uint64_t* pv_done, int q0, int head, int nb, int nblk,
-                                             int dn, uint32_t p_full_remote = 0, int crank = 0) {
+                                             int dn, uint32_t p_full_remote = 0, int crank = 0, int g0 = 0,
+                                             int* st_io = nullptr) {
+  // g0 / st_io (persistent kernels): the tile's first key block is block g0 of the CTA's flat block sequence (barrier
+  // phases continue across tiles), and the K/V ring stage is carried from tile to tile through *st_io
   const float sl = p.scale_log2;
   float m_run = -INFINITY;
   // The softmax denominator is never summed on the CUDA cores: a column of ones is written into the V tile at
@@ -82,11 +85,11 @@ __device__ __forceinline__ void softmax_tile(const AttnParams& p, int r, uint32_
   const int one_col = PAIR ? (p.d & 31) : (p.d & 63);
   const int one_slab = PAIR ? 0 : (p.d >> 6), one_chunk = one_col >> 3, one_elem = p.d & 7;
   const bool write_ones = PAIR ? ((p.d >> 5) == crank) : true;
-  int st = 0;
+  int st = st_io != nullptr ? *st_io : 0;
   for (int j = 0; j < nblk; ++j) {
     const int valid = min(kKV, p.s_kv - j * kKV);
     const int nchunk = (valid + 31) / 32;
-    mbar_wait(s_full, j & 1);
+    mbar_wait(s_full, (g0 + j) & 1);
     tc_fence_after();
     // pass 1: row max (full blocks take the mask-free path: the softmax warps are instruction-issue bound)
     float mx = -INFINITY;
@@ -121,7 +124,7 @@ __device__ __forceinline__ void softmax_tile(const AttnParams& p, int r, uint32_
     const float m_sl = m_new * sl;
     if (j > 0) {
       // previous P V must have retired before O is rescaled and P is overwritten
-      mbar_wait(pv_done, (j - 1) & 1);
+      mbar_wait(pv_done, (g0 + j - 1) & 1);
       tc_fence_after();
       if (!__all_sync(0xffffffffu, m_new == m_run)) {
         for (int c = 0; c < dn; c += 16) {
@@ -203,7 +206,8 @@ __device__ __forceinline__ void softmax_tile(const AttnParams& p, int r, uint32_
     }
   }
   // ---- epilogue: O / l -> global ----
-  mbar_wait(pv_done, (nblk - 1) & 1);
+  if (st_io != nullptr) *st_io = st;
+  mbar_wait(pv_done, (g0 + nblk - 1) & 1);
   tc_fence_after();
   float inv_l;
   {  // the denominator is the accumulator column d (one-column load: no register array to index at run time)
@@ -756,6 +760,198 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tc_fence_before();
   }
 
+  __syncthreads();
+  if (warp == 5) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent form of the one-tile kernel, for the head dims it serves (d = 80 / 160: DC = 2 / 3) where a (frame, head)
+// has only 1 - 3 key blocks: with one 128-row tile per CTA every CTA pays tensor-memory allocation, barrier set-up, the
+// full TMA latency of its first Q / K / V loads and the output tail for ~4 us of work (S = 384, d = 80: 1 152 CTAs,
+// 77 us for a 14 us floor). Here one CTA per SM walks a flat list of (query tile, head, frame) items: Q and the O
+// accumulator are double-buffered, the K/V ring, the MMA queue and every barrier phase run across item boundaries, so
+// the next item's loads and its first S = Q K^T overlap the current item's softmax tail and output.
+// Roles as in attention_tc_kernel (warps 0-3 softmax / output via softmax_tile, warp 4 TMA, warp 5 MMA).
+// ---------------------------------------------------------------------------------------------------------------
+template <int DC, int NS>
+constexpr int attnp1_smem_bytes() {
+  return (2 * DC + 2 * NS * DC + 2) * kSlab + 256;
+}
+struct AttnItems {
+  int n_qt, heads, n_items;  // items = n_qt * heads * n_batch, query tile fastest
+};
+
+template <int DC, int NS>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attention_persist1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                          const __grid_constant__ CUtensorMap tmV, const __grid_constant__ AttnParams p,
+                          const __grid_constant__ AttnItems pi) {
+  constexpr uint32_t kTmemCols = 512u;
+  constexpr uint32_t kOStride = DC <= 2 ? 128u : 192u;  // columns per O accumulator (dn <= 128 / 176)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint8_t* sQ = smem;                          // 2 x DC slabs: query tile of the current / next item
+  uint8_t* sK = sQ + 2 * DC * kSlab;           // NS x DC slabs
+  uint8_t* sV = sK + NS * DC * kSlab;          // NS x DC slabs
+  uint8_t* sP = sV + NS * DC * kSlab;          // 2 slabs (keys 0-63, 64-127)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kSlab);
+  uint64_t* q_full = bars;              // [2]
+  uint64_t* q_empty = q_full + 2;       // [2] the last QK of the item has read this Q buffer
+  uint64_t* kv_full = q_empty + 2;      // [NS]
+  uint64_t* kv_empty = kv_full + NS;    // [NS]
+  uint64_t* s_full = kv_empty + NS;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* pv_done = p_full + 1;
+  uint64_t* o_empty = pv_done + 1;      // [2] the output role has read this O accumulator
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int first = (int)blockIdx.x, step = (int)gridDim.x;
+  const int nblk = (p.s_kv + kKV - 1) / kKV;
+  const int dk16 = (p.d + 15) / 16;         // K-steps of S = Q K^T
+  const int dn = (p.d + 1 + 15) / 16 * 16;  // N of O = P [V | 1]
+  const int n_my = first < pi.n_items ? (pi.n_items - first + step - 1) / step : 0;
+  auto decode = [&](int item, int& q0, int& head, int& nb) {
+    q0 = (item % pi.n_qt) * kQ;
+    head = (item / pi.n_qt) % pi.heads;
+    nb = item / (pi.n_qt * pi.heads);
+  };
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&q_full[b], 1);
+      mbar_init(&q_empty[b], 1);
+      mbar_init(&o_empty[b], 128);
+    }
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc<kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_S = tmem_base;
+  const uint32_t tmem_O = tmem_base + 128;
+  griddep_sync();
+
+  if (warp == 4) {
+    if (role_elect()) {
+      // ===== TMA producer =====
+      int st = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < n_my; ++it) {
+        int q0, head, nb;
+        decode(first + it * step, q0, head, nb);
+        const int nkb = nb / p.kv_div;
+        const int qb = it & 1;
+        mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[qb], DC * kSlab);
+        for (int dc = 0; dc < DC; ++dc) tma_load_4d(sQ + (qb * DC + dc) * kSlab, &tmQ, &q_full[qb], dc * 64, head, q0, nb);
+        for (int j = 0; j < nblk; ++j) {
+          mbar_wait(&kv_empty[st], ph ^ 1);
+          mbar_expect_tx(&kv_full[st], 2 * DC * kSlab);
+          for (int dc = 0; dc < DC; ++dc) {
+            tma_load_4d(sK + (st * DC + dc) * kSlab, &tmK, &kv_full[st], dc * 64, head, j * kKV, nkb);
+            tma_load_4d(sV + (st * DC + dc) * kSlab, &tmV, &kv_full[st], dc * 64, head, j * kKV, nkb);
+          }
+          if (++st == NS) {
+            st = 0;
+            ph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (role_elect()) {
+      // ===== MMA issuer: flat block sequence g = it * nblk + j; S(g+1) is issued as soon as the softmax warps have
+      // consumed S(g) (they signal it with P(g)), i.e. before O += P(g) V(g) - across item boundaries too =====
+      const uint32_t idesc_pv = umma_idesc_f16(128, dn, 0, 1);  // B (= [V | 1]) is MN-major
+      const int total = n_my * nblk;
+      auto n16_of = [&](int j) { return (min(kKV, p.s_kv - j * kKV) + 15) / 16; };
+      int st_qk = 0, it_qk = 0, j_qk = 0;
+      uint32_t ph_qk = 0;
+      auto issue_qk = [&]() {  // S = Q(it_qk) K(j_qk)^T
+        const int qb = it_qk & 1;
+        if (j_qk == 0) {
+          mbar_wait(&q_full[qb], (it_qk >> 1) & 1);
+          tc_fence_after();
+        }
+        const uint32_t idesc_qk = umma_idesc_f16(128, n16_of(j_qk) * 16, 0, 0);
+        mbar_wait(&kv_full[st_qk], ph_qk);
+        tc_fence_after();
+        for (int ks = 0; ks < dk16; ++ks) {
+          const int dc = ks >> 2, kin = ks & 3;
+          const uint64_t qd = umma_desc_kmajor_sw128(smem_u32(sQ + (qb * DC + dc) * kSlab)) + 2 * kin;
+          const uint64_t kd = umma_desc_kmajor_sw128(smem_u32(sK + (st_qk * DC + dc) * kSlab)) + 2 * kin;
+          umma_f16_ss(tmem_S, qd, kd, idesc_qk, ks != 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+        if (++j_qk == nblk) {
+          umma_commit(&q_empty[qb]);  // Q buffer may be refilled
+          j_qk = 0;
+          ++it_qk;
+        }
+        if (++st_qk == NS) {
+          st_qk = 0;
+          ph_qk ^= 1;
+        }
+      };
+      if (total > 0) issue_qk();
+      int st = 0, it = 0, j = 0;
+      for (int g = 0; g < total; ++g) {
+        const int ob = it & 1;
+        if (j == 0 && it >= 2) {  // the output role must have drained this accumulator (item it - 2)
+          mbar_wait(&o_empty[ob], ((it >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        mbar_wait(p_full, g & 1);  // P(g) written, S(g) consumed
+        tc_fence_after();
+        if (g + 1 < total) issue_qk();
+        const int n16 = n16_of(j);
+        const uint32_t tO = tmem_O + ob * kOStride;
+        for (int kk = 0; kk < n16; ++kk) {
+          const uint64_t pd = umma_desc_kmajor_sw128(smem_u32(sP + (kk >> 2) * kSlab)) + 2 * (kk & 3);
+          const uint64_t vd = umma_desc_mnmajor_sw128(smem_u32(sV + st * DC * kSlab) + kk * 2048, kSlab);
+          umma_f16_ss(tO, pd, vd, idesc_pv, (j | kk) != 0 ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[st]);
+        umma_commit(pv_done);
+        if (++st == NS) st = 0;
+        if (++j == nblk) {
+          j = 0;
+          ++it;
+        }
+      }
+    }
+  } else {
+    // ===== softmax / correction / output: thread = query row; one softmax_tile per item with flat barrier phases =====
+    int st = 0;
+    for (int it = 0; it < n_my; ++it) {
+      int q0, head, nb;
+      decode(first + it * step, q0, head, nb);
+      const int ob = it & 1;
+      softmax_tile<DC, NS>(p, warp * 32 + lane, static_cast<uint32_t>(warp * 32) << 16, tmem_S, tmem_O + ob * kOStride, sP,
+                           sV, s_full, p_full, pv_done, q0, head, nb, nblk, dn, 0u, 0, it * nblk, &st);
+      tc_fence_before();
+      mbar_arrive(&o_empty[ob]);  // this thread's row of the accumulator has been read
+    }
+  }
+
+  tc_fence_before();
   __syncthreads();
   if (warp == 5) {
     __syncwarp();
@@ -1633,6 +1829,25 @@ static int launch_attn2(const CUtensorMap& tq, const CUtensorMap& tk, const CUte
 }
 
 template <int DC, int NS>
+static int launch_attn_persist1(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& ap,
+                                const AttnItems& pi, cudaStream_t stream) {
+  constexpr int smem = attnp1_smem_bytes<DC, NS>();
+  static_assert(smem <= 227 * 1024, "persistent one-tile attention exceeds shared memory");
+  auto kern = attention_persist1_kernel<DC, NS>;
+  static DeviceOnce configured;
+  static int n_sm = 148;
+  if (configured.first()) {
+    IVV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int dev = 0;
+    IVV_CHECK_CUDA(cudaGetDevice(&dev));
+    IVV_CHECK_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int ctas = pi.n_items < n_sm ? pi.n_items : n_sm;
+  IVV_CHECK_CUDA(launch_pdl(kern, dim3((unsigned)ctas), dim3(kAttnThreads), smem, stream, tq, tk, tv, ap, pi));
+  return 0;
+}
+
+template <int DC, int NS>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& ap,
                        dim3 grid, cudaStream_t stream) {
   constexpr int smem = attn_smem_bytes<DC, NS>();
@@ -1657,7 +1872,7 @@ namespace ivv {
 // kernels: persistent CTA pairs for d <= 62, the one-tile kernel otherwise.
 struct AttnEnv {
   int qk_first, mode, dbg;
-  bool pair, pair_short, poly, ns6, two_tile;
+  bool pair, pair_short, poly, ns6, two_tile, persist1;
 };
 static const AttnEnv& attn_env() {
   static const AttnEnv e = [] {
@@ -1671,6 +1886,7 @@ static const AttnEnv& attn_env() {
     a.pair_short = geti("IVV_ATTN_PAIR_SHORT", 1) != 0;
     a.poly = geti("IVV_ATTN_POLY", 0) != 0;
     a.ns6 = geti("IVV_ATTN_NS", 2) == 6;
+    a.persist1 = geti("IVV_ATTN_PERSIST1", 0) != 0;
 #ifdef IVV_TUNING
     a.mode = geti("IVV_ATTN_MODE", 3);
     a.dbg = geti("IVV_ATTN_DBG", 0);
@@ -1787,6 +2003,17 @@ extern "C" int ivv_attention(const void* q, int64_t q_ld, const void* k, const v
 #endif
   dim3 grid((unsigned)((s_q + kQ - 1) / kQ), (unsigned)heads, (unsigned)n_batch);
   if (dc == 1) return launch_attn<1, 2>(tq, tk, tv, ap, grid, stream);
+  // d = 80 / 160: persistent one-tile kernel once there are more items than SMs to amortise over (IVV_ATTN_PERSIST1=1
+  // for now: opt-in until measured)
+  const long long n_items = (long long)grid.x * heads * n_batch;
+  if (env.persist1 && n_items > 148 && n_items < (1LL << 30)) {
+    AttnItems pi{};
+    pi.n_qt = (int)grid.x;
+    pi.heads = heads;
+    pi.n_items = (int)n_items;
+    if (dc == 2) return launch_attn_persist1<2, 2>(tq, tk, tv, ap, pi, stream);
+    return launch_attn_persist1<3, 1>(tq, tk, tv, ap, pi, stream);
+  }
   if (dc == 2) return launch_attn<2, 2>(tq, tk, tv, ap, grid, stream);
   return launch_attn<3, 1>(tq, tk, tv, ap, grid, stream);
 }

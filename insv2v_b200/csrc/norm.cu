@@ -1,6 +1,8 @@
 // GroupNorm(+SiLU) and LayerNorm(+positional encoding) for channels-last fp16 activations. HBM-bound kernels:
 // 16-byte vector loads, fp32 per-thread partials, deterministic double-precision cross-CTA merge (statistics match
 // the fp32 reference to ~1e-7). Reference call sites: ivv.h (K6/K7/K8).
+#include <cstdlib>
+
 #include "../../include/ivv.h"
 #include "common.cuh"
 
@@ -15,6 +17,14 @@ namespace ivv {
 // The ticket counters wrap back to zero by themselves (atomicInc with the chunk count as the limit), so a workspace
 // that was zero when first used stays usable call after call without a memset node in front of every norm.
 // ------------------------------------------------------------------------------------------------
+#ifndef IVV_GN_LOADS_STATS
+#define IVV_GN_LOADS_STATS 8
+#endif
+#ifndef IVV_GN_LOADS_APPLY
+#define IVV_GN_LOADS_APPLY 4  // 8 costs 108 registers (two CTAs per SM)
+#endif
+// 16-byte loads a thread keeps in flight (tuning: tools/build_variant.sh x -DIVV_GN_LOADS_APPLY=8)
+constexpr int kGnLoads = IVV_GN_LOADS_STATS, kGnLoadsApply = IVV_GN_LOADS_APPLY;
 struct GnWs {
   unsigned int* counters;
   float2* final_;   // (mean, rstd)
@@ -28,12 +38,58 @@ __host__ __device__ inline size_t gn_counter_bytes(long long n_bg) {
   return (size_t)(b < kGnSelfCleanBytes ? kGnSelfCleanBytes : b);
 }
 
+// In-CTA reduction of the per-thread partials s_part[R][C] (sum, sum of squares) to one pair per group, in a fixed order
+// and spread over the CTA: every channel first sums its R row lanes (s_ch[C]), then a group is summed by one warp
+// (lanes stride over the group's channels, shuffle tree) or, for narrow groups, by one thread. (One thread per group
+// walking R x C/groups shared-memory values was a serial tail of up to ~3 000 clk per CTA.) Ends with a __syncthreads
+// after the s_ch pass only; the caller orders the writes of `emit`.
+template <class Emit>
+__device__ __forceinline__ void gn_reduce_cta(const float2* s_part, float2* s_ch, int R, int C, int groups, Emit&& emit) {
+  const int cpg = C / groups;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int rr = 0; rr < R; ++rr) {
+      const float2 v = s_part[rr * C + c];
+      a += v.x;
+      b += v.y;
+    }
+    s_ch[c] = make_float2(a, b);
+  }
+  __syncthreads();
+  if (cpg >= 16) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (int)blockDim.x >> 5;  // full warps only (the block size need not be a multiple of 32)
+    if (warp < nwarps) {
+      for (int g = warp; g < groups; g += nwarps) {
+        float a = 0.f, b = 0.f;
+        for (int c = lane; c < cpg; c += 32) {
+          const float2 v = s_ch[g * cpg + c];
+          a += v.x;
+          b += v.y;
+        }
+        a = warp_sum(a);
+        b = warp_sum(b);
+        if (lane == 0) emit(g, a, b);
+      }
+    }
+  } else {
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+      float a = 0.f, b = 0.f;
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        a += s_ch[c].x;
+        b += s_ch[c].y;
+      }
+      emit(g, a, b);
+    }
+  }
+}
+
 // Two-source form (x2 != nullptr): channels [0, C1) come from x [.., C1], channels [C1, C) from x2 [.., C - C1] - the
 // skip concatenation of the up blocks (unet_blocks.py:561,659) read in place instead of being materialised.
 __global__ void gn_stats_kernel(const __half* __restrict__ x, const __half* __restrict__ x2, int C1, GnWs ws,
                                 long long rows_per_bg, int C, int groups, long long rows_per_cta, int V, int R,
                                 float eps) {
-  extern __shared__ __align__(16) float s_part[];  // [R][C][2]
+  extern __shared__ __align__(16) float s_part[];  // [R][C][2] | [C][2] (gn_reduce_cta)
   __shared__ bool s_last;
   griddep_sync();
   const int bg = blockIdx.y;
@@ -51,12 +107,12 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, const __half* __re
     const long long ld = x2 == nullptr ? C : (second ? C - C1 : C1);
     const __half* base = (second ? x2 + (vec * 8 - C1) : x + vec * 8) + ((long long)bg * rows_per_bg) * ld;
     long long r = row_begin + rsub;
-    for (; r + 3LL * R < row_end; r += 4LL * R) {
-      uint4 u[4];
+    for (; r + (long long)(kGnLoads - 1) * R < row_end; r += (long long)kGnLoads * R) {
+      uint4 u[kGnLoads];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(base + (r + (long long)k * R) * ld);
+      for (int k = 0; k < kGnLoads; ++k) u[k] = *reinterpret_cast<const uint4*>(base + (r + (long long)k * R) * ld);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < kGnLoads; ++k) {
         const __half2* h = reinterpret_cast<const __half2*>(&u[k]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -87,16 +143,10 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, const __half* __re
     }
   }
   __syncthreads();
-  // fixed-order in-CTA reduction: thread g sums its group's channels over all row lanes
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    float a = 0.f, b = 0.f;
-    for (int rr = 0; rr < R; ++rr)
-      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-        a += s_part[(rr * C + c) * 2];
-        b += s_part[(rr * C + c) * 2 + 1];
-      }
-    ws.partial[((long long)bg * ws.max_chunks + blockIdx.x) * groups + g] = make_float2(a, b);
-  }
+  gn_reduce_cta(reinterpret_cast<const float2*>(s_part), reinterpret_cast<float2*>(s_part) + (size_t)R * C, R, C, groups,
+                [&](int g, float a, float b) {
+                  ws.partial[((long long)bg * ws.max_chunks + blockIdx.x) * groups + g] = make_float2(a, b);
+                });
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -211,16 +261,171 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, __half* __restrict
     return o;
   };
   long long r = row_begin + rsub;
-  for (; r + 3LL * R < row_end; r += 4LL * R) {
-    uint4 u[4];
+  for (; r + (long long)(kGnLoadsApply - 1) * R < row_end; r += (long long)kGnLoadsApply * R) {
+    uint4 u[kGnLoadsApply];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(xb + (r + (long long)k * R) * ld);
+    for (int k = 0; k < kGnLoadsApply; ++k) u[k] = *reinterpret_cast<const uint4*>(xb + (r + (long long)k * R) * ld);
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < kGnLoadsApply; ++k)
       *reinterpret_cast<uint4*>(yb + (r + (long long)k * R) * C) = xform(u[k], r + (long long)k * R);
   }
   for (; r < row_end; r += R)
     *reinterpret_cast<uint4*>(yb + r * C) = xform(*reinterpret_cast<const uint4*>(xb + r * ld), r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm in ONE kernel, for tensors that fit in the shared memory of the chip (one CTA per SM, <= kGnFusedSmem each):
+// the two-kernel form above is launch- and dependency-latency bound on the small levels of the UNet (4608 x 1280:
+// 2 x 9.5 us for 11.8 MB, 18432 x 640: 2 x 14 us, profiles/r02_graph_timeline_final.txt). Here a CTA reads its rows ONCE,
+// keeps them in shared memory, publishes its per-group partial sums (same workspace and ticket counter as
+// gn_stats_kernel), WAITS until every CTA of its batch group has done so, merges the partials itself (every CTA in the
+// same fixed order, double precision: identical statistics everywhere, no second hop through a "last CTA") and
+// normalises out of shared memory.
+// The wait: the ticket counter wraps to zero on the last arrival (atomicInc with limit chunks - 1), and a CTA that has
+// arrived sees a non-zero counter until then - so "counter == 0 after my own arrival" means "all partials published",
+// and the counter is back at zero for the next launch without a reset. All CTAs of the grid are co-resident by
+// construction (grid <= SM count, one CTA per SM; a programmatic dependent launch only starts once every CTA here has
+// started), so the spin cannot deadlock.
+// ------------------------------------------------------------------------------------------------
+constexpr int kGnFusedSmem = 208 * 1024;
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(512, 1)
+gn_fused_kernel(const __half* __restrict__ x, const __half* __restrict__ x2, int C1, __half* __restrict__ y,
+                const __half* __restrict__ gamma, const __half* __restrict__ beta, GnWs ws, long long rows_per_bg, int C,
+                int groups, int rows_per_cta, int V, int R, float eps, int act) {
+  extern __shared__ __align__(16) uint8_t gsm[];  // [rows_per_cta][V] uint4 | [R][C] float2 | [C] float2
+  __shared__ float2 s_final[64];
+  uint4* tile = reinterpret_cast<uint4*>(gsm);
+  float2* s_part = reinterpret_cast<float2*>(gsm + (size_t)rows_per_cta * C * 2);
+  float2* s_ch = s_part + (size_t)R * C;
+  griddep_sync();
+  const int bg = blockIdx.y;
+  const int chunks = gridDim.x;
+  const long long row_begin = (long long)blockIdx.x * rows_per_cta;
+  const int nrows = (int)(min(rows_per_bg, row_begin + rows_per_cta) - row_begin);
+  const int vec = threadIdx.x % V;
+  const int rsub = threadIdx.x / V;
+  const int cpg = C / groups;
+  const bool second = x2 != nullptr && vec * 8 >= C1;
+  const long long ld = x2 == nullptr ? C : (second ? C - C1 : C1);
+  const __half* base = (second ? x2 + (vec * 8 - C1) : x + vec * 8) + ((long long)bg * rows_per_bg + row_begin) * ld;
+  // ---- pass 1: global -> shared memory + per-thread partial sums (thread = one 8-channel column, every R-th row) ----
+  if (rsub < R) {
+    float s[8], ss[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+    auto acc = [&](const uint4& u) {
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        s[2 * j] += f.x;
+        ss[2 * j] = fmaf(f.x, f.x, ss[2 * j]);
+        s[2 * j + 1] += f.y;
+        ss[2 * j + 1] = fmaf(f.y, f.y, ss[2 * j + 1]);
+      }
+    };
+    int r = rsub;
+    for (; r + 7 * R < nrows; r += 8 * R) {  // eight 16-byte loads in flight per thread
+      uint4 u[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) u[k] = *reinterpret_cast<const uint4*>(base + (long long)(r + k * R) * ld);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        tile[(r + k * R) * V + vec] = u[k];
+        acc(u[k]);
+      }
+    }
+    for (; r < nrows; r += R) {
+      const uint4 u = *reinterpret_cast<const uint4*>(base + (long long)r * ld);
+      tile[r * V + vec] = u;
+      acc(u);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_part[rsub * C + vec * 8 + j] = make_float2(s[j], ss[j]);
+  }
+  __syncthreads();
+  // ---- in-CTA reduction (fixed order, spread over the CTA) -> this CTA's partials ----
+  gn_reduce_cta(s_part, s_ch, R, C, groups, [&](int g, float a, float b) {
+    ws.partial[((long long)bg * ws.max_chunks + blockIdx.x) * groups + g] = make_float2(a, b);
+  });
+  __threadfence();
+  __syncthreads();
+  // ---- arrive, then wait for the batch group (see the note above) ----
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicInc(&ws.counters[bg], (unsigned int)chunks - 1);  // wraps to 0 on the last arrival
+    if (t != (unsigned int)chunks - 1) {
+      while (ld_acquire_u32(&ws.counters[bg]) != 0u) __nanosleep(20);
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  // ---- every CTA merges the partials of its batch group: fixed order, double precision ----
+  {
+    const int L = max(1, (int)blockDim.x / groups);
+    double2* s_lane = reinterpret_cast<double2*>(s_part);  // [L][groups]; the row partials are no longer needed
+    const int g = threadIdx.x % groups, l = threadIdx.x / groups;
+    if (l < L) {
+      double a = 0.0, b = 0.0;
+#pragma unroll 4
+      for (int ch = l; ch < chunks; ch += L) {
+        const float2 pv = __ldcg(&ws.partial[((long long)bg * ws.max_chunks + ch) * groups + g]);
+        a += (double)pv.x;
+        b += (double)pv.y;
+      }
+      s_lane[l * groups + g] = make_double2(a, b);
+    }
+    __syncthreads();
+    if (threadIdx.x < groups) {
+      const double inv_n = 1.0 / ((double)rows_per_bg * cpg);
+      double a = 0.0, b = 0.0;
+      for (int ll = 0; ll < L; ++ll) {
+        a += s_lane[ll * groups + threadIdx.x].x;
+        b += s_lane[ll * groups + threadIdx.x].y;
+      }
+      const double mean = a * inv_n;
+      double var = b * inv_n - mean * mean;
+      if (var < 0) var = 0;
+      s_final[threadIdx.x] = make_float2((float)mean, (float)(1.0 / sqrt(var + (double)eps)));
+    }
+    __syncthreads();
+  }
+  // ---- pass 2: normalise out of shared memory (each thread re-reads exactly what it wrote) ----
+  if (rsub >= R) return;
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = vec * 8 + j;
+    const float2 mr = s_final[c / cpg];
+    a[j] = mr.y * __half2float(gamma[c]);
+    b[j] = __half2float(beta[c]) - mr.x * a[j];
+  }
+  __half* yb = y + ((long long)bg * rows_per_bg + row_begin) * C + vec * 8;
+  for (int r = rsub; r < nrows; r += R) {
+    const uint4 u = tile[r * V + vec];
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      float v0 = fmaf(f.x, a[2 * j], b[2 * j]);
+      float v1 = fmaf(f.y, a[2 * j + 1], b[2 * j + 1]);
+      if (act == 1) {
+        v0 = silu_f(v0);
+        v1 = silu_f(v1);
+      } else if (act == 2) {
+        v0 = fmaxf(v0, 0.f);
+        v1 = fmaxf(v1, 0.f);
+      }
+      oh[j] = __floats2half2_rn(v0, v1);
+    }
+    *reinterpret_cast<uint4*>(yb + (long long)r * C) = o;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -357,10 +562,47 @@ extern "C" size_t ivv_groupnorm_ws_bytes(int64_t n_img, int32_t groups, int64_t 
 }
 
 namespace ivv {
+// IVV_GN_FUSED=0 keeps the two-kernel GroupNorm everywhere (tuning hook; read once)
+static bool gn_fused_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("IVV_GN_FUSED");
+    return v == nullptr || atoi(v) != 0;
+  }();
+  return on;
+}
+static int gn_sm_count() {  // of the current device (cached per device ordinal)
+  static int n[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  if (n[dev] == 0 && cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n[dev] = 0;
+  return n[dev];
+}
+// one-kernel GroupNorm (gn_fused_kernel): at most one CTA per SM, each holding its rows in shared memory
+struct GnFusedPlan {
+  int chunks, rows_per_cta, R;
+  size_t smem;
+};
+static bool gn_fused_plan(long long n_bg, long long rows_per_bg, long long c, int groups, GnFusedPlan* out) {
+  if (!gn_fused_enabled() || groups > 64 || c % 8 != 0) return false;
+  const int sms = gn_sm_count();
+  const int V = (int)(c / 8);
+  const int R = V >= 512 ? 1 : 512 / V;
+  if (n_bg <= 0 || n_bg > sms || V * R > 512 || V * R < groups) return false;
+  const long long chunks = sms / n_bg;  // one CTA per SM at most: the CTAs wait for each other
+  const long long rpc = (rows_per_bg + chunks - 1) / chunks;
+  const long long nch = (rows_per_bg + rpc - 1) / rpc;
+  const size_t smem = (size_t)rpc * c * 2 + (size_t)(R + 1) * c * 2 * sizeof(float);
+  if (smem > (size_t)kGnFusedSmem || rpc >= (1LL << 20)) return false;
+  out->chunks = (int)nch;
+  out->rows_per_cta = (int)rpc;
+  out->R = R;
+  out->smem = smem;
+  return true;
+}
 static int groupnorm_impl(const void* x, void* y, const void* gamma, const void* beta, int64_t n_img, int64_t hw,
                           int64_t c, int32_t groups, int64_t frames_per_group, float eps, int32_t act,
                           const void* residual, void* stats_ws, size_t stats_ws_bytes, int max_groups,
-                          cudaStream_t stream, const void* x2 = nullptr, int64_t c1 = 0) {
+                          cudaStream_t stream, const void* x2 = nullptr, int64_t c1 = 0, bool allow_fused = false) {
   IVV_REQUIRE(x2 == nullptr || (c1 > 0 && c1 < c && c1 % 8 == 0), "ivv_groupnorm2: c1 (%lld) must be a multiple of 8 in (0, c)",
               (long long)c1);
   IVV_REQUIRE(x && y && stats_ws, "ivv_groupnorm: null pointer");
@@ -385,6 +627,20 @@ static int groupnorm_impl(const void* x, void* y, const void* gamma, const void*
   // more batch groups than the self-cleaning region covers: counters beyond it may alias older final/partial data
   if (n_bg * 4 > kGnSelfCleanBytes) IVV_CHECK_CUDA(cudaMemsetAsync(stats_ws, 0, gn_counter_bytes(n_bg), stream));
   const int V = (int)(c / 8);
+  // ---- one-kernel form: the whole tensor in the shared memory of the chip (see gn_fused_kernel) ----
+  GnFusedPlan fp;
+  if (allow_fused && residual == nullptr && gamma != nullptr && beta != nullptr && gn_fused_plan(n_bg, rows_per_bg, c, groups, &fp) &&
+      fp.chunks <= ws.max_chunks) {
+    static DeviceOnce configured;
+    if (configured.first())
+      IVV_CHECK_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGnFusedSmem));
+    IVV_CHECK_CUDA(launch_pdl(gn_fused_kernel, dim3((unsigned)fp.chunks, (unsigned)n_bg), dim3((unsigned)(V * fp.R)),
+                              fp.smem, stream, reinterpret_cast<const __half*>(x), reinterpret_cast<const __half*>(x2),
+                              (int)c1, reinterpret_cast<__half*>(y), reinterpret_cast<const __half*>(gamma),
+                              reinterpret_cast<const __half*>(beta), ws, rows_per_bg, (int)c, groups, fp.rows_per_cta, V,
+                              fp.R, eps, (int)act));
+    return 0;
+  }
   const int R = V >= 256 ? 1 : 256 / V;
   const int threads = V * R;
   {
@@ -395,10 +651,10 @@ static int groupnorm_impl(const void* x, void* y, const void* gamma, const void*
     chunks = (rows_per_bg + rows_per_cta - 1) / rows_per_cta;
     IVV_REQUIRE(chunks <= ws.max_chunks, "ivv_groupnorm: internal chunking error");
     dim3 grid((unsigned)chunks, (unsigned)n_bg);
-    const size_t smem = (size_t)R * c * 2 * sizeof(float);
+    const size_t smem = (size_t)(R + 1) * c * 2 * sizeof(float);
     static DeviceOnce configured;  // per device (cudaFuncSetAttribute is a per-device attribute)
     if (smem > 48 * 1024 && configured.first())
-      IVV_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      IVV_CHECK_CUDA(cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 144 * 1024));
     IVV_CHECK_CUDA(launch_pdl(gn_stats_kernel, grid, dim3(threads), smem, stream, reinterpret_cast<const __half*>(x),
                               reinterpret_cast<const __half*>(x2), (int)c1, ws, rows_per_bg, (int)c, groups,
                               rows_per_cta, V, R, eps));
@@ -419,12 +675,20 @@ static int groupnorm_impl(const void* x, void* y, const void* gamma, const void*
 }
 }  // namespace ivv
 
+// 1 if ivv_groupnorm / ivv_groupnorm2 on this shape run as ONE kernel (launch accounting of the host side)
+extern "C" int ivv_groupnorm_is_fused(int64_t n_img, int64_t hw, int64_t c, int32_t groups, int64_t frames_per_group) {
+  if (frames_per_group <= 0 || n_img <= 0 || n_img % frames_per_group != 0 || groups <= 0) return 0;
+  const long long n_bg = n_img / frames_per_group;
+  ivv::GnFusedPlan fp;
+  return ivv::gn_fused_plan(n_bg, frames_per_group * hw, c, groups, &fp) && fp.chunks <= ivv::gn_max_chunks(n_bg) ? 1 : 0;
+}
+
 extern "C" int ivv_groupnorm2(const void* x1, int64_t c1, const void* x2, int64_t c2, void* y, const void* gamma,
                               const void* beta, int64_t n_img, int64_t hw, int32_t groups, int64_t frames_per_group,
                               float eps, int32_t silu, void* stats_ws, size_t stats_ws_bytes, ivv_stream_t stream_) {
   IVV_REQUIRE(gamma && beta && x2, "ivv_groupnorm2: null pointer");
   return ivv::groupnorm_impl(x1, y, gamma, beta, n_img, hw, c1 + c2, groups, frames_per_group, eps, silu ? 1 : 0,
-                             nullptr, stats_ws, stats_ws_bytes, 64, reinterpret_cast<cudaStream_t>(stream_), x2, c1);
+                             nullptr, stats_ws, stats_ws_bytes, 64, reinterpret_cast<cudaStream_t>(stream_), x2, c1, true);
 }
 
 extern "C" int ivv_groupnorm(const void* x, void* y, const void* gamma, const void* beta, int64_t n_img, int64_t hw,
@@ -432,7 +696,7 @@ extern "C" int ivv_groupnorm(const void* x, void* y, const void* gamma, const vo
                              void* stats_ws, size_t stats_ws_bytes, ivv_stream_t stream_) {
   IVV_REQUIRE(gamma && beta, "ivv_groupnorm: null pointer");
   return ivv::groupnorm_impl(x, y, gamma, beta, n_img, hw, c, groups, frames_per_group, eps, silu ? 1 : 0, nullptr,
-                             stats_ws, stats_ws_bytes, 64, reinterpret_cast<cudaStream_t>(stream_));
+                             stats_ws, stats_ws_bytes, 64, reinterpret_cast<cudaStream_t>(stream_), nullptr, 0, true);
 }
 
 // Per-channel normalisation over imgs_per_group images: InstanceNorm2d (imgs_per_group = 1) and BatchNorm2d with

@@ -39,6 +39,7 @@ SIGNATURES = {
     "ivv_groupnorm": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, c_i32, c_i64, c_f32, c_i32,
                               c_void_p, c_size, c_void_p]),
     "ivv_groupnorm_ws_bytes": (c_size, [c_i64, c_i32, c_i64]),
+    "ivv_groupnorm_is_fused": (c_i32, [c_i64, c_i64, c_i64, c_i32, c_i64]),
     "ivv_groupnorm2": (c_i32, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i32, c_i64,
                                c_f32, c_i32, c_void_p, c_size, c_void_p]),
     "ivv_layernorm": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_f32, c_void_p, c_i64, c_i64,

@@ -309,7 +309,7 @@ def groupnorm(x, gamma, beta, n_img, hw, groups, frames_per_group, eps, silu, ou
     _lib.check(L.ivv_groupnorm(_p(x), _p(out), _p(gamma), _p(beta), n_img, hw, c, groups, frames_per_group,
                                float(eps), int(silu), _p(ws), ws.numel(), _s()), "ivv_groupnorm")
     Prof.end(e0, ("groupnorm", n_img * hw, c, frames_per_group), 0.0, 6.0 * n_img * hw * c)
-    _lib.LAUNCH_COUNT += 2
+    _lib.LAUNCH_COUNT += 1 if L.ivv_groupnorm_is_fused(n_img, hw, c, groups, frames_per_group) else 2
     return out
 
 
@@ -327,7 +327,7 @@ def groupnorm2(x1, x2, gamma, beta, n_img, hw, groups, frames_per_group, eps, si
     _lib.check(L.ivv_groupnorm2(_p(x1), c1, _p(x2), c2, _p(out), _p(gamma), _p(beta), n_img, hw, groups,
                                 frames_per_group, float(eps), int(silu), _p(ws), ws.numel(), _s()), "ivv_groupnorm2")
     Prof.end(e0, ("groupnorm", n_img * hw, c1 + c2, frames_per_group), 0.0, 6.0 * n_img * hw * (c1 + c2))
-    _lib.LAUNCH_COUNT += 2
+    _lib.LAUNCH_COUNT += 1 if L.ivv_groupnorm_is_fused(n_img, hw, c1 + c2, groups, frames_per_group) else 2
     return out
 
 

@@ -247,7 +247,12 @@ def test_conv3x3_stride2(n, c, co, h, w):
 # ------------------------------------------------------------------------------------------------ norms
 @pytest.mark.parametrize("b,f,c,h,w,fpg,silu", [(3, 16, 320, 32, 48, 16, True), (2, 4, 640, 8, 12, 1, False),
                                                 (1, 2, 2560, 4, 6, 2, True), (2, 3, 128, 5, 7, 3, True),
-                                                (1, 4, 512, 16, 16, 1, True)])
+                                                (1, 4, 512, 16, 16, 1, True),
+                                                # the UNet's small levels at full size: the one-kernel form (whole tensor
+                                                # in shared memory, csrc/norm.cu gn_fused_kernel)
+                                                (3, 16, 1280, 8, 12, 16, True), (3, 16, 1280, 8, 12, 1, True),
+                                                (3, 16, 640, 16, 24, 1, True), (3, 16, 640, 16, 24, 16, False),
+                                                (3, 16, 1280, 4, 6, 16, True), (3, 8, 1280, 4, 4, 1, True)])
 def test_groupnorm(b, f, c, h, w, fpg, silu):
     ops = _ops()
     x = (h16(b * f, c, h, w, seed=1).float() * 1.5 + 0.3).half()
@@ -265,7 +270,8 @@ def test_groupnorm(b, f, c, h, w, fpg, silu):
 
 
 @pytest.mark.parametrize("b,f,c1,c2,h,w,fpg", [(2, 4, 320, 320, 8, 12, 4), (1, 6, 1280, 640, 4, 6, 6), (3, 2, 64, 128, 16, 16, 1),
-                                                (1, 16, 640, 320, 16, 24, 16)])
+                                                (1, 16, 640, 320, 16, 24, 16), (3, 16, 1280, 1280, 8, 12, 16),
+                                                (3, 16, 1280, 1280, 4, 6, 16)])
 def test_groupnorm_two_sources_equals_concat(b, f, c1, c2, h, w, fpg):
     """ivv_groupnorm2 reads the skip concatenation [x1 | x2] in place (unet_blocks.py:561,659 + resnet.py:177): it must
     give BIT-identical results to ivv_groupnorm on the materialised concatenation, and match torch."""
