@@ -920,7 +920,8 @@ attention_persist1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         }
         mbar_wait(p_full, g & 1);  // P(g) written, S(g) consumed
         tc_fence_after();
-        if (g + 1 < total) issue_qk();
+        // with a one-stage ring the next block's K/V can only be loaded once P V(g) has released the stage: QK after PV
+        if (NS >= 2 && g + 1 < total) issue_qk();
         const int n16 = n16_of(j);
         const uint32_t tO = tmem_O + ob * kOStride;
         for (int kk = 0; kk < n16; ++kk) {
@@ -930,6 +931,7 @@ attention_persist1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         }
         umma_commit(&kv_empty[st]);
         umma_commit(pv_done);
+        if (NS < 2 && g + 1 < total) issue_qk();
         if (++st == NS) st = 0;
         if (++j == nblk) {
           j = 0;
@@ -1886,7 +1888,7 @@ static const AttnEnv& attn_env() {
     a.pair_short = geti("IVV_ATTN_PAIR_SHORT", 1) != 0;
     a.poly = geti("IVV_ATTN_POLY", 0) != 0;
     a.ns6 = geti("IVV_ATTN_NS", 2) == 6;
-    a.persist1 = geti("IVV_ATTN_PERSIST1", 0) != 0;
+    a.persist1 = geti("IVV_ATTN_PERSIST1", 1) != 0;
 #ifdef IVV_TUNING
     a.mode = geti("IVV_ATTN_MODE", 3);
     a.dbg = geti("IVV_ATTN_DBG", 0);
@@ -2003,8 +2005,9 @@ extern "C" int ivv_attention(const void* q, int64_t q_ld, const void* k, const v
 #endif
   dim3 grid((unsigned)((s_q + kQ - 1) / kQ), (unsigned)heads, (unsigned)n_batch);
   if (dc == 1) return launch_attn<1, 2>(tq, tk, tv, ap, grid, stream);
-  // d = 80 / 160: persistent one-tile kernel once there are more items than SMs to amortise over (IVV_ATTN_PERSIST1=1
-  // for now: opt-in until measured)
+  // d = 80 / 160: persistent one-tile kernel once there are more items than SMs to amortise over (in the graph of a
+  // forward: S = 384 d = 80 76.9 -> 62.5 us, its 77-key cross-attention 43.9 -> 32.9 us, d = 160 18.7 / 18.3 -> 16.3 /
+  // 15.4 us; profiles/r02_attention_persist1_ab.txt). IVV_ATTN_PERSIST1=0 goes back to one tile per CTA (tuning hook).
   const long long n_items = (long long)grid.x * heads * n_batch;
   if (env.persist1 && n_items > 148 && n_items < (1LL << 30)) {
     AttnItems pi{};

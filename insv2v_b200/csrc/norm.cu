@@ -31,7 +31,13 @@ struct GnWs {
   float2* partial;  // (sum, sumsq)
   int max_chunks;
 };
-__host__ __device__ inline int gn_max_chunks(long long n_bg) { return (int)(148 * 4 / n_bg) + 2; }
+#ifndef IVV_GN_STATS_CPS
+#define IVV_GN_STATS_CPS 4  // statistics CTAs per SM (tuning: tools/build_variant.sh x -DIVV_GN_STATS_CPS=2)
+#endif
+#ifndef IVV_GN_APPLY_CPS
+#define IVV_GN_APPLY_CPS 8
+#endif
+__host__ __device__ inline int gn_max_chunks(long long n_bg) { return (int)(148 * IVV_GN_STATS_CPS / n_bg) + 2; }
 constexpr long long kGnSelfCleanBytes = 4096;  // counter region the caller zero-fills once (n_bg <= 1024)
 __host__ __device__ inline size_t gn_counter_bytes(long long n_bg) {
   const long long b = (n_bg * 4 + 255) / 256 * 256;
@@ -645,7 +651,7 @@ static int groupnorm_impl(const void* x, void* y, const void* gamma, const void*
   const int threads = V * R;
   {
     // ~4 CTAs per SM in total, at least 8 row sweeps per CTA, never more chunks than the workspace holds
-    long long chunks = (148 * 4 + n_bg - 1) / n_bg;
+    long long chunks = (148 * IVV_GN_STATS_CPS + n_bg - 1) / n_bg;
     long long rows_per_cta = (rows_per_bg + chunks - 1) / chunks;
     if (rows_per_cta < 8LL * R) rows_per_cta = 8LL * R;
     chunks = (rows_per_bg + rows_per_cta - 1) / rows_per_cta;
@@ -660,7 +666,7 @@ static int groupnorm_impl(const void* x, void* y, const void* gamma, const void*
                               rows_per_cta, V, R, eps));
   }
   {
-    long long chunks2 = (148 * 8 + n_bg - 1) / n_bg;
+    long long chunks2 = (148 * IVV_GN_APPLY_CPS + n_bg - 1) / n_bg;
     long long rpc = (rows_per_bg + chunks2 - 1) / chunks2;
     if (rpc < 4LL * R) rpc = 4LL * R;
     chunks2 = (rows_per_bg + rpc - 1) / rpc;

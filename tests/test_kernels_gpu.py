@@ -355,6 +355,32 @@ def test_self_attention_peaky(s_q, s_kv, d, gain):
     report(f"peaky self-attn sq{s_q} skv{s_kv} d{d}", out.reshape(n, s_q, c), ref, rtol=2e-3, atol=5e-4 * gain)
 
 
+@pytest.mark.parametrize("n,s_q,s_kv,heads,d,kv_div,gain", [
+    (48, 384, 384, 8, 80, 1, 1.0),     # UNet level 1 self-attention: 1 152 items of 3 key blocks
+    (48, 96, 96, 8, 160, 1, 1.0),      # level 2: one block per item, one-stage K/V ring
+    (48, 384, 77, 8, 80, 16, 1.0),     # cross-attention: masked single block, K/V shared by 16 frames
+    (48, 96, 77, 8, 160, 16, 1.0),
+    (40, 200, 300, 8, 80, 1, 2.0),     # ragged query tile, masked last block, jumping row maxima (O rescale)
+    (30, 130, 129, 8, 160, 1, 2.0),    # two query tiles / two key blocks with one valid row / key in the second
+    (150, 24, 24, 8, 160, 1, 1.0),     # 4x6 level shape, more items than SMs
+])
+def test_attention_persistent_one_tile(n, s_q, s_kv, heads, d, kv_div, gain):
+    """d = 80 / 160 with more (query tile, head, frame) items than SMs: the persistent one-tile kernel
+    (csrc/attention_tc.cu attention_persist1_kernel; Q / O double buffering and barrier phases across items)."""
+    ops = _ops()
+    c = heads * d
+    q = h16(n * s_q, c, scale=gain, seed=1)
+    kv = h16(n // kv_div * s_kv, 2 * c, scale=gain, seed=2)
+    out = ops.attention(q, kv[:, :c], kv[:, c:], n_batch=n, s_q=s_q, s_kv=s_kv, heads=heads, d=d, q_ld=c, kv_ld=2 * c,
+                        kv_div=kv_div)
+    k, v = (t.float().reshape(n // kv_div, s_kv, c).repeat_interleave(kv_div, dim=0) for t in kv.chunk(2, dim=-1))
+    ref = _sdpa_ref(q.float().reshape(n, s_q, c), k, v, heads)
+    report(f"persistent one-tile attn n{n} sq{s_q} skv{s_kv} d{d}", out.reshape(n, s_q, c), ref, rtol=2e-3, atol=5e-4 * gain)
+    out2 = ops.attention(q, kv[:, :c], kv[:, c:], n_batch=n, s_q=s_q, s_kv=s_kv, heads=heads, d=d, q_ld=c, kv_ld=2 * c,
+                         kv_div=kv_div)
+    assert torch.equal(out, out2)
+
+
 @pytest.mark.parametrize("clips,frames,s,heads,d", [(3, 4, 384, 8, 80), (2, 3, 1536, 8, 40), (2, 2, 24, 8, 160)])
 def test_cross_attention(clips, frames, s, heads, d):
     ops = _ops()

@@ -9,7 +9,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 # (n_batch, s_q, s_kv, heads, d, kv_div)
-SHAPES = [(48, 1536, 1536, 8, 40, 1), (48, 1536, 77, 8, 40, 16), (48, 384, 384, 8, 80, 1), (48, 96, 96, 8, 160, 1)]
+SHAPES = [(48, 1536, 1536, 8, 40, 1), (48, 1536, 77, 8, 40, 16), (48, 384, 384, 8, 80, 1), (48, 96, 96, 8, 160, 1),
+          (48, 384, 77, 8, 80, 16), (48, 96, 77, 8, 160, 16), (48, 24, 24, 8, 160, 1)]
 VARIANTS = [
     {"IVV_ATTN_PAIR": "0"},
     {"IVV_ATTN_PAIR": "1", "IVV_ATTN_MODE": "3"},
@@ -18,6 +19,9 @@ VARIANTS = [
 ]
 if os.environ.get("ATTN_BENCH_ONE"):
     SHAPES = SHAPES[:2]
+if os.environ.get("ATTN_BENCH_SMALL"):  # the d = 80 / 160 shapes only, default vs the persistent one-tile kernel
+    SHAPES = SHAPES[2:]
+    VARIANTS = [{}, {"IVV_ATTN_PERSIST1": "1"}]
 
 
 def child():

@@ -74,6 +74,12 @@ x0, g0, b0 = h16(N * 1536, 320), h16(320), h16(320)
 add(lambda: ops.groupnorm(x0, g0, b0, N, 1536, 32, 16, 1e-5, True))
 add(lambda: ops.groupnorm(x0, g0, b0, N, 1536, 32, 1, 1e-6, False))
 add(lambda: ops.layernorm(x0, g0, b0))
+# one-kernel GroupNorm (gn_fused_kernel): the 16x24 and 8x12 levels, per-frame and 16-frame statistics
+x1n, g1n = h16(N * 384, 640), h16(640)
+add(lambda: ops.groupnorm(x1n, g1n, g1n, N, 384, 32, 1, 1e-6, False))
+add(lambda: ops.groupnorm(x1n, g1n, g1n, N, 384, 32, 16, 1e-5, True))
+x2n, g2n = h16(N * 96, 1280), h16(1280)
+add(lambda: ops.groupnorm(x2n, g2n, g2n, N, 96, 32, 16, 1e-5, True))
 x2, g2, pe = h16(N * 96, 1280), h16(1280), f32(32, 1280)
 add(lambda: ops.layernorm(x2, g2, g2, pe=pe, rows_per_frame=96, frames=16, pe_start=0))
 wd = ops.pack_conv3x3_im2col(h16(320, 320, 3, 3, scale=0.02))

@@ -54,6 +54,7 @@ def geglu(rows, c):
 
 run("GEGLU 2000x320", lambda: geglu(2000, 320))
 run("GEGLU 300x1280", lambda: geglu(300, 1280))
+run("GEGLU 6000x320 (several tiles per cluster: staged bias, two output slabs)", lambda: geglu(6000, 320))
 
 
 def conv(n, ci, co, h, w, res=False, rowbias=False, f32out=False):
@@ -87,10 +88,16 @@ run("attention cross 77 keys d=40 (kv_div)", lambda: attn(4, 1536, 77, 8, 40, kv
 run("attention one-tile d=80 S=384", lambda: attn(4, 384, 384, 8, 80))
 run("attention one-tile d=160 S=96", lambda: attn(4, 96, 96, 8, 160))
 run("attention ragged S=100 d=40", lambda: attn(3, 100, 100, 8, 40))
+run("attention persistent one-tile d=80 S=384 (576 items)", lambda: attn(24, 384, 384, 8, 80))
+run("attention persistent one-tile d=160 77 keys (kv_div)", lambda: attn(48, 96, 77, 8, 160, kv_div=16))
 for fr in (16, 24, 64):
     run(f"temporal attention F={fr}", lambda fr=fr: ops.temporal_attention(h16(2 * fr * 24, 3 * 320), 2, fr, 24, 320, 8))
 
 # ---- norms -------------------------------------------------------------------------------------------------------------
+run("groupnorm two-kernel form (more batch groups than SMs)",
+    lambda: ops.groupnorm(h16(160 * 24, 320), h16(320), h16(320), 160, 24, 32, 1, 1e-5, True))
+run("groupnorm one-kernel form, two sources", lambda: ops.groupnorm2(h16(8 * 96, 640), h16(8 * 96, 320), h16(960), h16(960),
+                                                                     8, 96, 32, 4, 1e-5, True))
 run("groupnorm 5-D + SiLU", lambda: ops.groupnorm(h16(2 * 4 * 384, 320), h16(320), h16(320), 8, 384, 32, 4, 1e-5, True))
 run("groupnorm per frame", lambda: ops.groupnorm(h16(6 * 96, 1280), h16(1280), h16(1280), 6, 96, 32, 1, 1e-6, False))
 run("layernorm C=320", lambda: ops.layernorm(h16(5000, 320), h16(320), h16(320)))
