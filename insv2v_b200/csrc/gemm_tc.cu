@@ -359,6 +359,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   // of tile i+1 is requested when the epilogue of tile i STARTS and has a whole tile period to land.
   static_assert(!DS || TILEWIDE, "double staging belongs to the tile-wide epilogues");
   static_assert(!GEGLU || (TILEWIDE && CW == 32 && BN == 256), "GEGLU epilogue: tile-wide staging, 32-column chunks");
+  // WIDE (BN = 320, pair mode): the tile is two 160-wide halves that share the activation tile -- two N = 160 MMAs per
+  // k-step into ONE 320-column accumulator (2 x 320 fp32 columns do not fit the 512 of TMEM, so the accumulator is not
+  // double-buffered: the epilogue of a tile is exposed, which only pays for long main loops). The N = 1280 layers of the
+  // 8x12 level (36 M tiles) are 72 such tiles = ONE wave of the 74 clusters; as 160- / 256-wide tiles they are 144 / 90 = two
+  // rounds, and fetch the activation rows 8 / 5 times instead of 4.
+  constexpr bool kWide = BN > 256;
+  static_assert(!kWide || (BN == 320 && TWO && !HALO && !GEGLU && !TILEWIDE && !DS && CW == 32),
+                "320-wide tiles: pair mode, ring staging, 32-column chunks");
   constexpr int kBRows = TWO ? BN / 2 : BN;
   constexpr int kBTileBytes = kBRows * 128;
   constexpr int kAOff = HALO ? kHaloBytes : kABytes;  // offset of the weight tile(s) inside a stage
@@ -369,8 +377,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   const int tile_step = CS > 1 ? (int)num_clusters_x() : (int)gridDim.x;
   constexpr int kChunkBytes = kBlockM * CW * 2;  // one [128 rows x CW fp16] swizzled slab per column chunk
   constexpr int kStagingBytes = TILEWIDE ? kBlockM * (GEGLU ? BN / 2 : BN) * 2 : 2 * kChunkBytes;
-  constexpr uint32_t kAccStride = acc_stride_for<BN>();
-  constexpr uint32_t kTmemCols = 2 * kAccStride;
+  constexpr uint32_t kAccStride = kWide ? 0u : acc_stride_for<BN>();
+  constexpr uint32_t kTmemCols = kWide ? 512u : 2 * kAccStride;
+  // accumulator buffer and barrier parity of the CTA's local-th tile (WIDE: one buffer, its barriers flip every tile)
+  auto acc_buf = [](int local_) { return kWide ? 0 : (local_ & 1); };
+  auto acc_phase = [](int local_) { return static_cast<uint32_t>(kWide ? (local_ & 1) : ((local_ >> 1) & 1)); };
   uint8_t* staging = smem + STAGES * kStageBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + (DS ? 2 : 1) * kStagingBytes);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -479,7 +490,15 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
             if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);
             tma_load_4d_2sm(sa, &tmA, lead_bar, kb * kBlockK, w0 + dx, h0 + dy, n0);
-            tma_load_3d_2sm(sa + kABytes, &tmB, lead_bar, kb * kBlockK, ntile * BN + crank * kBRows, tap);
+            if constexpr (kWide) {
+              // weight rows of this CTA: its quarter of each 160-wide half (tmB's box is BN / 4 rows), so that the pair's
+              // MMA h sees the rows [h * 160, h * 160 + 160) of the tile in order
+              tma_load_3d_2sm(sa + kABytes, &tmB, lead_bar, kb * kBlockK, ntile * BN + crank * (BN / 4), tap);
+              tma_load_3d_2sm(sa + kABytes + (BN / 4) * 128, &tmB, lead_bar, kb * kBlockK,
+                              ntile * BN + BN / 2 + crank * (BN / 4), tap);
+            } else {
+              tma_load_3d_2sm(sa + kABytes, &tmB, lead_bar, kb * kBlockK, ntile * BN + crank * kBRows, tap);
+            }
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -520,14 +539,14 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   } else if (warp == 1) {
     if ((!TWO || crank == 0) && role_elect()) {
       // ===== MMA issuer (pair mode: the leader CTA issues for both) =====
-      constexpr uint32_t idesc = umma_idesc_f16(TWO ? 2 * kBlockM : kBlockM, BN, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_f16(TWO ? 2 * kBlockM : kBlockM, kWide ? BN / 2 : BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
       if (ws) mbar_wait(b_full, 0);
       for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++local) {
-        const int buf = local & 1;
-        mbar_wait(&tmem_empty_bar[buf], ((local >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        const int buf = acc_buf(local);
+        mbar_wait(&tmem_empty_bar[buf], acc_phase(local) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         stamp(local, 2);
         const uint32_t tacc = tmem_base + buf * kAccStride;
@@ -556,8 +575,15 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             if (p.dbg_skip == 1 && (it | k) != 0) continue;
-            if constexpr (TWO) umma_f16_ss_2sm(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
-            else umma_f16_ss(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+            if constexpr (kWide) {
+              const uint64_t bdesc_hi = umma_desc_kmajor_sw128(sa + kABytes + (BN / 4) * 128);
+              umma_f16_ss_2sm(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+              umma_f16_ss_2sm(tacc + BN / 2, adesc + 2 * k, bdesc_hi + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+            } else if constexpr (TWO) {
+              umma_f16_ss_2sm(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+            } else {
+              umma_f16_ss(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+            }
           }
           if constexpr (TWO) umma_commit_2sm(&empty_bar[stage], kMask);
           else if constexpr (CS > 1) umma_commit_multicast(&empty_bar[stage], kMask);
@@ -645,7 +671,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       const bool valid = (w < p.W) && (h < p.H) && (n < p.NI);
       const long long pix = (static_cast<long long>(n) * p.H + h) * p.W + w;
       const __half* rb = (p.rowbias && valid) ? p.rowbias + (pix / p.rowbias_group) * p.rowbias_ld : nullptr;
-      const int buf = local & 1;
+      const int buf = acc_buf(local);
       const bool etr = issuer && g == 0;
       if (etr) stamp(local, 4);
       if constexpr (TILEWIDE) {
@@ -671,7 +697,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         if (!has_res) named_bar_sync(1 + g, 128);
       }
       if (etr) stamp(local, 5);
-      mbar_wait(&tmem_full_bar[buf], (local >> 1) & 1);
+      mbar_wait(&tmem_full_bar[buf], acc_phase(local));
       tc_fence_after();
       if (etr) stamp(local, 6);
       if constexpr (TILEWIDE) {
@@ -1672,7 +1698,7 @@ namespace ivv {
 // -1 = unset. IVV_HALO / IVV_DS / IVV_EPI2 / IVV_PAIR: 0 disables; IVV_CLUSTER=2, IVV_FORCE_BN=32|64|128|160|256,
 // IVV_NO_WS=1, IVV_DEBUG_SKIP=1..5 (knock-outs, results are garbage).
 struct GemmEnv {
-  int halo, ds, epi2, pair, cluster, force_bn, no_ws, ws, dbg_skip, geglu_ds, cl4, cl4_min;
+  int halo, ds, epi2, pair, cluster, force_bn, no_ws, ws, dbg_skip, geglu_ds, cl4, cl4_min, wide;
 };
 static const GemmEnv& gemm_env() {
   static const GemmEnv e = [] {
@@ -1693,6 +1719,7 @@ static const GemmEnv& gemm_env() {
     g.geglu_ds = geti("IVV_GEGLU_DS");
     g.cl4 = geti("IVV_CL4");
     g.cl4_min = geti("IVV_CL4_MIN");
+    g.wide = geti("IVV_WIDE");
     return g;
   }();
   return e;
@@ -1722,6 +1749,10 @@ extern "C" int ivv_debug_conv_box(int64_t w, int64_t h, int64_t n_img, int32_t w
 
 // tuning hook: how many 4-CTA clusters of the short-K pair kernel the current device runs at once (0 = unavailable)
 extern "C" int ivv_debug_cl4_clusters() { return ivv::pair160_cl4_clusters<5>(); }
+
+// tuning / test hook (not in ivv.h): tile width (BLOCK_N) the calling thread's last ivv_gemm chose
+static thread_local int g_last_bn = 0;
+extern "C" int ivv_debug_last_gemm_tile() { return g_last_bn; }
 
 static long long* g_gemm_trace = nullptr;
 // tuning only: clock64 trace of CTA 0 of the next persistent-kernel launches into buf ([32 tiles][16] int64); NULL = off
@@ -1866,7 +1897,27 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
   kp.ln_eps = a->ln_eps;
   kp.ln_inv_c = 1.f / (float)a->c;
   if (ds || pair160) bn_sel = 160;
+  // 320-wide tiles (pair kernel, two N = 160 MMAs per k-step, one accumulator): taken when the tile list then needs fewer
+  // rounds of the 74 clusters. Cost model in clocks per (tap, k-block) of a tile, calibrated on B200
+  // (profiles/r02_gemm_wide_ab.txt): 950 for the 320-wide tile, 840 / 772 for 256 / 160; the 320-wide tile also pays its
+  // epilogue in the open (one accumulator): ~7 000 clk, ~14 000 with a residual (fetched chunk by chunk).
+  // The N = 1280 convolutions and the FF out-projection of the 8x12 level: 72 tiles = one round instead of 144 = two.
+  // IVV_WIDE=0 disables, IVV_FORCE_BN=320 takes it wherever it is legal (tuning hooks).
+  if (!a->geglu && !halo && !ds && !pair160 && persistent_ok && m_tiles >= 2 && (a->n_out % 320) == 0 &&
+      (long long)a->c * a->taps >= 2560 && a->splits <= 1 && env.pair < 0 && env.cluster < 0 && env.no_ws < 0 &&
+      (env.force_bn < 0 || env.force_bn == 320) && env.wide != 0) {
+    const long long clusters = sm_count() / 2, pairs = (m_tiles + 1) / 2;
+    const double its = (double)kp.taps * kp.kblocks;
+    auto cost = [&](int bn) {
+      const long long nt = (a->n_out + bn - 1) / bn;
+      const long long rounds = (pairs * nt + clusters - 1) / clusters;
+      const double per_it = bn == 320 ? 950.0 : bn == 256 ? 840.0 : bn == 160 ? 772.0 : 700.0;
+      return (double)rounds * (its * per_it + (bn == 320 ? (a->residual ? 14000.0 : 7000.0) : 0.0));
+    };
+    if (env.force_bn == 320 || cost(320) < 0.95 * cost(bn_sel)) bn_sel = 320;
+  }
   const int n_tiles = (int)((a->n_out + bn_sel - 1) / bn_sel);
+  g_last_bn = bn_sel;
 
   // ---- tensor maps ----
   CUtensorMap tmA, tmB, tmB2;
@@ -1880,9 +1931,10 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
   {
     const uint64_t dims[3] = {(uint64_t)a->c, (uint64_t)a->n_out, (uint64_t)a->taps};
     const uint64_t strides[3] = {2, (uint64_t)a->w_ld * 2, (uint64_t)a->w_ld * 2 * a->n_out};
-    const uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)bn_sel, 1};
+    const uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)(bn_sel > 256 ? 256 : bn_sel), 1};  // (unused by the 320-wide tiles)
     if (int rc = make_tmap_f16(&tmB, a->wgt, 3, dims, strides, box, 128)) return rc;
-    const uint32_t box2[3] = {(uint32_t)kBlockK, (uint32_t)(bn_sel / 2), 1};  // half tile per CTA of a 2-CTA cluster
+    // half tile per CTA of a 2-CTA cluster (320-wide tiles: a quarter per load, two loads per CTA)
+    const uint32_t box2[3] = {(uint32_t)kBlockK, (uint32_t)(bn_sel == 320 ? 80 : bn_sel / 2), 1};
     if (int rc = make_tmap_f16(&tmB2, a->wgt, 3, dims, strides, box2, 128)) return rc;
   }
 
@@ -1980,6 +2032,7 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
         IVV_PAIR_LAUNCH(256, 6, 32, true, true);
       }
       switch (bn_sel) {
+        case 320: IVV_PAIR_LAUNCH(320, 5, 32, false, false);
         case 256:
           if (k_total >= 2560) IVV_PAIR_LAUNCH(256, 6, 64, false, false);
           IVV_PAIR_LAUNCH(256, 5, 64, false, true);
@@ -1990,6 +2043,7 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
       }
 #undef IVV_PAIR_LAUNCH
     }
+    IVV_REQUIRE(bn_sel != 320, "ivv_gemm: internal: 320-wide tile chosen outside the pair kernel");
     if (a->geglu) return launch_persistent<256, 4, 32, true, true>(tmA, tmB2, tmB, tmD, tmR, kp, m_tiles, n_tiles, cs, stream);
     switch (bn_sel) {
       case 256:

@@ -90,64 +90,12 @@ __device__ __forceinline__ void gn_reduce_cta(const float2* s_part, float2* s_ch
   }
 }
 
-// Two-source form (x2 != nullptr): channels [0, C1) come from x [.., C1], channels [C1, C) from x2 [.., C - C1] - the
-// skip concatenation of the up blocks (unet_blocks.py:561,659) read in place instead of being materialised.
-__global__ void gn_stats_kernel(const __half* __restrict__ x, const __half* __restrict__ x2, int C1, GnWs ws,
-                                long long rows_per_bg, int C, int groups, long long rows_per_cta, int V, int R,
-                                float eps) {
-  extern __shared__ __align__(16) float s_part[];  // [R][C][2] | [C][2] (gn_reduce_cta)
-  __shared__ bool s_last;
-  griddep_sync();
-  const int bg = blockIdx.y;
-  const int chunks = gridDim.x;
-  const long long row_begin = (long long)blockIdx.x * rows_per_cta;
-  const long long row_end = min(rows_per_bg, row_begin + rows_per_cta);
-  const int vec = threadIdx.x % V;
-  const int rsub = threadIdx.x / V;
+// Tail shared by the statistics kernels: per-CTA partials (fixed-order reduction of s_part[R][C]) -> workspace, ticket, and
+// the merge by the last CTA of the batch group. Must be reached by every thread of the CTA.
+__device__ __forceinline__ void gn_stats_finish(float* s_part, bool* s_last_p, const GnWs& ws, int bg, int chunks,
+                                                long long rows_per_bg, int C, int groups, int R, float eps) {
+  bool& s_last = *s_last_p;
   const int cpg = C / groups;
-  float s[8], ss[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
-  if (rsub < R) {
-    const bool second = x2 != nullptr && vec * 8 >= C1;
-    const long long ld = x2 == nullptr ? C : (second ? C - C1 : C1);
-    const __half* base = (second ? x2 + (vec * 8 - C1) : x + vec * 8) + ((long long)bg * rows_per_bg) * ld;
-    long long r = row_begin + rsub;
-    for (; r + (long long)(kGnLoads - 1) * R < row_end; r += (long long)kGnLoads * R) {
-      uint4 u[kGnLoads];
-#pragma unroll
-      for (int k = 0; k < kGnLoads; ++k) u[k] = *reinterpret_cast<const uint4*>(base + (r + (long long)k * R) * ld);
-#pragma unroll
-      for (int k = 0; k < kGnLoads; ++k) {
-        const __half2* h = reinterpret_cast<const __half2*>(&u[k]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __half22float2(h[j]);
-          s[2 * j] += f.x;
-          ss[2 * j] = fmaf(f.x, f.x, ss[2 * j]);
-          s[2 * j + 1] += f.y;
-          ss[2 * j + 1] = fmaf(f.y, f.y, ss[2 * j + 1]);
-        }
-      }
-    }
-    for (; r < row_end; r += R) {
-      const uint4 u = *reinterpret_cast<const uint4*>(base + r * ld);
-      const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(h[j]);
-        s[2 * j] += f.x;
-        ss[2 * j] = fmaf(f.x, f.x, ss[2 * j]);
-        s[2 * j + 1] += f.y;
-        ss[2 * j + 1] = fmaf(f.y, f.y, ss[2 * j + 1]);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s_part[((rsub * C) + vec * 8 + j) * 2] = s[j];
-      s_part[((rsub * C) + vec * 8 + j) * 2 + 1] = ss[j];
-    }
-  }
   __syncthreads();
   gn_reduce_cta(reinterpret_cast<const float2*>(s_part), reinterpret_cast<float2*>(s_part) + (size_t)R * C, R, C, groups,
                 [&](int g, float a, float b) {
@@ -207,6 +155,67 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, const __half* __re
     }
     finish(g, a, b);
   }
+}
+
+// Two-source form (x2 != nullptr): channels [0, C1) come from x [.., C1], channels [C1, C) from x2 [.., C - C1] - the
+// skip concatenation of the up blocks (unet_blocks.py:561,659) read in place instead of being materialised.
+__global__ void gn_stats_kernel(const __half* __restrict__ x, const __half* __restrict__ x2, int C1, GnWs ws,
+                                long long rows_per_bg, int C, int groups, long long rows_per_cta, int V, int R,
+                                float eps) {
+  extern __shared__ __align__(16) float s_part[];  // [R][C][2] | [C][2] (gn_reduce_cta)
+  __shared__ bool s_last;
+  griddep_sync();
+  const int bg = blockIdx.y;
+  const int chunks = gridDim.x;
+  const long long row_begin = (long long)blockIdx.x * rows_per_cta;
+  const long long row_end = min(rows_per_bg, row_begin + rows_per_cta);
+  const int vec = threadIdx.x % V;
+  const int rsub = threadIdx.x / V;
+  const int cpg = C / groups;
+  float s[8], ss[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+  if (rsub < R) {
+    const bool second = x2 != nullptr && vec * 8 >= C1;
+    const long long ld = x2 == nullptr ? C : (second ? C - C1 : C1);
+    const __half* base = (second ? x2 + (vec * 8 - C1) : x + vec * 8) + ((long long)bg * rows_per_bg) * ld;
+    long long r = row_begin + rsub;
+    for (; r + (long long)(kGnLoads - 1) * R < row_end; r += (long long)kGnLoads * R) {
+      uint4 u[kGnLoads];
+#pragma unroll
+      for (int k = 0; k < kGnLoads; ++k) u[k] = *reinterpret_cast<const uint4*>(base + (r + (long long)k * R) * ld);
+#pragma unroll
+      for (int k = 0; k < kGnLoads; ++k) {
+        const __half2* h = reinterpret_cast<const __half2*>(&u[k]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h[j]);
+          s[2 * j] += f.x;
+          ss[2 * j] = fmaf(f.x, f.x, ss[2 * j]);
+          s[2 * j + 1] += f.y;
+          ss[2 * j + 1] = fmaf(f.y, f.y, ss[2 * j + 1]);
+        }
+      }
+    }
+    for (; r < row_end; r += R) {
+      const uint4 u = *reinterpret_cast<const uint4*>(base + r * ld);
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        s[2 * j] += f.x;
+        ss[2 * j] = fmaf(f.x, f.x, ss[2 * j]);
+        s[2 * j + 1] += f.y;
+        ss[2 * j + 1] = fmaf(f.y, f.y, ss[2 * j + 1]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s_part[((rsub * C) + vec * 8 + j) * 2] = s[j];
+      s_part[((rsub * C) + vec * 8 + j) * 2 + 1] = ss[j];
+    }
+  }
+  gn_stats_finish(s_part, &s_last, ws, bg, chunks, rows_per_bg, C, groups, R, eps);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -603,6 +603,81 @@ def test_conv3x3_splitk(n, ci, co, h, w):
     assert torch.equal(out, out2)  # fixed-order reduction: bit-reproducible
 
 
+@pytest.mark.parametrize("n,ci,co,h,w,fused", [(48, 1280, 1280, 8, 12, True), (48, 640, 1280, 8, 12, False),
+                                               (48, 320, 1280, 8, 12, True)])
+def test_conv3x3_wide_tiles(n, ci, co, h, w, fused):
+    """The N = 1280 convolutions of the 8x12 level run as 320-wide tiles (two N = 160 MMAs per k-step on one
+    accumulator): 72 tiles = one round of the 74 clusters. Same fused terms as every other epilogue."""
+    from insv2v_b200 import lib
+    ops = _ops()
+    x = h16(n, ci, h, w, seed=1)
+    wt = h16(co, ci, 3, 3, scale=(9 * ci) ** -0.5, seed=2)
+    b, res, temb = h16(co, seed=3), h16(n, co, h, w, seed=5), h16(3, co, seed=4)
+    f = n // 3
+    kw = dict(rowbias=temb, rowbias_group=f * h * w, residual=_frames(res)) if fused else {}
+    out = ops.conv3x3(_frames(x), ops.pack_conv3x3(wt), n, h, w, bias=b, **kw)
+    assert lib.load().ivv_debug_last_gemm_tile() == 320
+    ref = F.conv2d(x.double(), wt.double(), b.double(), padding=1)
+    if fused:
+        ref = ref + res.double() + temb.double().repeat_interleave(f, dim=0)[:, :, None, None]
+    report(f"conv3x3 wide {ci}->{co} {h}x{w}", _nchw(out, n, h, w), ref)
+    out2 = ops.conv3x3(_frames(x), ops.pack_conv3x3(wt), n, h, w, bias=b, **kw)
+    assert torch.equal(out, out2)
+
+
+def test_linear_wide_tiles():
+    """FF out-projection of the 8x12 level (4608 x 5120 -> 1280 + residual): 320-wide tiles, one round."""
+    from insv2v_b200 import lib
+    ops = _ops()
+    rows, k, n = 4608, 5120, 1280
+    x, w, b, res = h16(rows, k, seed=1), h16(n, k, scale=k ** -0.5, seed=2), h16(n, seed=3), h16(rows, n, seed=4)
+    out = ops.linear(x, ops.pack_linear(w), bias=b, residual=res)
+    assert lib.load().ivv_debug_last_gemm_tile() == 320
+    report("linear wide 4608x5120x1280", out, x.double() @ w.double().t() + b.double() + res.double())
+
+
+_WIDE_SNIPPET = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from insv2v_b200 import ops, lib
+torch.manual_seed(0)
+dev = "cuda"
+fr = lambda t: t.permute(0, 2, 3, 1).reshape(-1, t.shape[1]).contiguous()
+# several tiles per cluster (the single accumulator's barriers flip every tile), ragged last M tile, odd number of M tiles
+for rows, k, n, with_res in [(128 * 157 + 50, 2560, 640, True), (128 * 301, 2624, 320, False), (300, 2560, 960, True)]:
+    x = torch.randn(rows, k, device=dev).half(); w = (torch.randn(n, k, device=dev) * k ** -0.5).half()
+    b = torch.randn(n, device=dev).half(); r = torch.randn(rows, n, device=dev).half() if with_res else None
+    o = ops.linear(x, ops.pack_linear(w), bias=b, residual=r)
+    assert lib.load().ivv_debug_last_gemm_tile() == 320, (rows, k, n)
+    ref = x.double() @ w.double().t() + b.double() + (r.double() if with_res else 0)
+    err = (o.double() - ref).abs()
+    assert (err <= 1e-4 + 1e-3 * ref.abs()).all(), (rows, k, n, float(err.max()))
+    assert torch.equal(o, ops.linear(x, ops.pack_linear(w), bias=b, residual=r))
+# per-tap convolution with a ragged box (5 frames of 8x12: 3.75 M tiles) and a channel tail (ci %% 64 != 0)
+n, ci, co, h, w = 5, 328, 640, 8, 12
+x = torch.randn(n, ci, h, w, device=dev).half(); wt = (torch.randn(co, ci, 3, 3, device=dev) * (9 * ci) ** -0.5).half()
+b = torch.randn(co, device=dev).half(); res = torch.randn(n, co, h, w, device=dev).half()
+out = ops.conv3x3(fr(x), ops.pack_conv3x3(wt), n, h, w, bias=b, residual=fr(res))
+assert lib.load().ivv_debug_last_gemm_tile() == 320
+ref = torch.nn.functional.conv2d(x.double(), wt.double(), b.double(), padding=1) + res.double()
+err = (out.reshape(n, h, w, co).permute(0, 3, 1, 2).double() - ref).abs()
+assert (err <= 1e-4 + 1e-3 * ref.abs()).all(), float(err.max())
+print("wide ok")
+"""
+
+
+def test_wide_tiles_forced():
+    """IVV_FORCE_BN=320 takes the 320-wide tile wherever it is legal: tile lists longer than the cluster count, ragged
+    and ghost tiles, a per-tap convolution with a clipped box."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _WIDE_SNIPPET % root], env=dict(os.environ, IVV_FORCE_BN="320"),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "wide ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 # ------------------------------------------------------------------------------------------------ frame I/O
 def test_frame_io_matches_the_reference_transform(tmp_path):
     """video_io: uint8 frames -> [-1, 1] tensors bit-identical to the reference's cv2.cvtColor + ToTensor + Normalize

@@ -20,6 +20,12 @@ SHAPES = [
     (1, 1, 73728, 320, 320, 1, True), (1, 1, 18432, 640, 640, 1, True), (1, 1, 4608, 1280, 1280, 1, True),
     (1, 1, 73728, 1280, 320, 1, True), (1, 1, 18432, 2560, 640, 1, True), (1, 1, 1152, 1280, 1280, 1, True),
 ]
+# GEMM_AB_ONLY=wide: the shapes the 320-wide pair tiles are meant for (and two they must not slow down)
+WIDE_SHAPES = [
+    (48, 8, 12, 1280, 1280, 9, True), (48, 8, 12, 2560, 1280, 9, False), (48, 8, 12, 1920, 1280, 9, False),
+    (48, 8, 12, 640, 1280, 9, False), (1, 1, 4608, 5120, 1280, 1, True), (1, 1, 18432, 2560, 640, 1, True),
+    (1, 1, 73728, 2880, 320, 1, False),
+]
 SETTINGS = [dict(IVV_HALO="0"), dict(IVV_HALO="1")]
 # temporal attention (clips, frames, pixels, channels): the four UNet levels
 TATTN = [(3, 16, 1536, 320), (3, 16, 384, 640), (3, 16, 96, 1280), (3, 16, 24, 1280)]
@@ -30,7 +36,7 @@ def child():
     dev = torch.device("cuda")
     tag = " ".join(f"{k[4:]}={v}" for k, v in sorted(os.environ.items()) if k.startswith("IVV_"))
     only = os.environ.get("GEMM_AB_ONLY", "")  # "linear": the 1x1 shapes only, "conv": the 3x3 ones, "none": neither
-    for n, h, w, c, n_out, taps, res in SHAPES:
+    for n, h, w, c, n_out, taps, res in (WIDE_SHAPES if only == "wide" else SHAPES):
         if (only == "linear" and taps != 1) or (only == "conv" and taps == 1) or only == "none":
             continue
         rows = n * h * w
