@@ -237,6 +237,13 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta_rank
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// TMA prefetch of a 4-D box into L2 (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 // TMA loads of a CTA pair: data lands in the issuing CTA's shared memory, the bytes are counted on `bar_cluster_addr`
 // (the leader's barrier)
 __device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,

@@ -34,6 +34,7 @@ struct GemmKParams {
                                   // 4 = no residual term, 5 = no epilogue work (results are garbage)
   long long* trace;               // tuning only (ivv_debug_gemm_trace): clock64 stamps of CTA 0, [tile][16]
   int halo_bytes;                 // HALO kernels: bytes of one (bw x (bh + 2)) activation box = (bh + 2) * bw * 128
+  int as_prefetch;                // AS modes: prefetch the activation rows of the cluster's NEXT M pair into L2
   void* d;
   long long d_ld;
   const __half* bias;
@@ -334,7 +335,8 @@ constexpr int persist_smem_bytes() {
          (GEGLU ? kGegluBiasBytes : 0);
 }
 
-template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, int CS, bool TWO, bool HALO = false, bool DS = false>
+template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, int CS, bool TWO, bool HALO = false, bool DS = false,
+          bool AS = false>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                           const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
@@ -359,6 +361,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   // of tile i+1 is requested when the epilogue of tile i STARTS and has a whole tile period to land.
   static_assert(!DS || TILEWIDE, "double staging belongs to the tile-wide epilogues");
   static_assert(!GEGLU || (TILEWIDE && CW == 32 && BN == 256), "GEGLU epilogue: tile-wide staging, 32-column chunks");
+  // AS (activation-stationary, pair mode, at most STAGES K blocks per tile: the K = 320 GEGLU GEMM of the 32x48 level): as
+  // in gemm_tc_pair160_kernel<.., AS>, a cluster takes ALL N tiles of an M pair; the activation parts of the stages hold
+  // the pair's rows for the whole M pair (slice it in stage it), only the weight parts cycle. With K = 320 a tile needs
+  // the whole ring, so in the plain mode every tile pays a load round trip; here only weights (L2-resident) are in flight.
+  static_assert(!AS || (TWO && !HALO && BN <= 256), "activation-stationary mode is built on the plain pair kernel");
   // WIDE (BN = 320, pair mode): the tile is two 160-wide halves that share the activation tile -- two N = 160 MMAs per
   // k-step into ONE 320-column accumulator (2 x 320 fp32 columns do not fit the 512 of TMEM, so the accumulator is not
   // double-buffered: the epilogue of a tile is exposed, which only pays for long main loops). The N = 1280 layers of the
@@ -375,6 +382,19 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   const int crank = CS > 1 ? (int)cluster_ctarank() : 0;
   const int tile_first = CS > 1 ? (int)cluster_id_x() : (int)blockIdx.x;
   const int tile_step = CS > 1 ? (int)num_clusters_x() : (int)gridDim.x;
+  // tiles of this CTA / cluster, in order: round robin over the M-major tile list; AS: the M pairs tile_first,
+  // tile_first + tile_step, ... with all their N tiles
+  const int as_groups = total_tiles / n_tiles;
+  const int n_local = AS ? (tile_first < as_groups ? ((as_groups - tile_first + tile_step - 1) / tile_step) * n_tiles : 0)
+                         : (tile_first < total_tiles ? (total_tiles - tile_first + tile_step - 1) / tile_step : 0);
+  auto tile_of = [&](int l) -> int {
+    if constexpr (AS) {
+      const int j = l / n_tiles;
+      return (tile_first + j * tile_step) * n_tiles + (l - j * n_tiles);
+    } else {
+      return tile_first + l * tile_step;
+    }
+  };
   constexpr int kChunkBytes = kBlockM * CW * 2;  // one [128 rows x CW fp16] swizzled slab per column chunk
   constexpr int kStagingBytes = TILEWIDE ? kBlockM * (GEGLU ? BN / 2 : BN) * 2 : 2 * kChunkBytes;
   constexpr uint32_t kAccStride = kWide ? 0u : acc_stride_for<BN>();
@@ -389,7 +409,10 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;  // [2]
   uint64_t* res_bar = tmem_empty_bar + 2;        // [2 groups][2 slabs] residual tile landed (single slab: [g] only)
   uint64_t* b_full = res_bar + 4;                // weight-stationary mode: resident weight tile landed
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
+  uint64_t* a_full = b_full + 1;                 // AS [STAGES]: resident activation slice landed (leader counts both CTAs)
+  uint64_t* a_empty = a_full + STAGES;           // AS [STAGES]: the last N tile of the M pair has read the slice
+  static_assert(!AS || (4 * STAGES + 9) * 8 + 4 <= 256, "barrier block");
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(AS ? a_empty + STAGES : b_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -416,6 +439,12 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       mbar_init(&res_bar[2 + b], 1);
     }
     mbar_init(b_full, 1);
+    if constexpr (AS) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&a_full[s], 1);
+        mbar_init(&a_empty[s], 1);
+      }
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -448,8 +477,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           tma_load_3d(b_res + it * (BN * 128), &tmB, b_full, (it - tap * p.kblocks) * kBlockK, ntile0 * BN, tap);
         }
       }
-      int plocal = 0;
-      for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++plocal) {
+      for (int plocal = 0; plocal < n_local; ++plocal) {
+        const int tile = tile_of(plocal);
         const int ntile = tile % n_tiles;
         const int mtile = (tile / n_tiles) * CS + crank;
         const int tw = mtile % p.tiles_w;
@@ -465,6 +494,15 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           if (p.taps > 1) {
             dy = tap / p.tap_w - (p.tap_h >> 1);
             dx = tap % p.tap_w - (p.tap_w >> 1);
+          }
+          if constexpr (AS) {
+            if (ntile == 0) {  // first N tile of an M pair: (re)load the resident activation slice of this K block
+              const uint32_t jpar = (uint32_t)(plocal / n_tiles) & 1u;
+              mbar_wait(&a_empty[it], jpar ^ 1u);
+              const uint32_t lead_a = mapa_shared(smem_u32(&a_full[it]), 0);
+              if (crank == 0) mbar_expect_tx(&a_full[it], 2 * kABytes);
+              tma_load_4d_2sm(smem + it * kStageBytes, &tmA, lead_a, kb * kBlockK, w0 + dx, h0 + dy, n0);
+            }
           }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
@@ -488,8 +526,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             // bytes of BOTH CTAs are counted on the leader's barrier. The peer needs no arrive of its own: it can only
             // refill a stage after the leader's MMA released it, i.e. after the leader's barrier finished that phase.
             const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), 0);
-            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * kStageBytes);
-            tma_load_4d_2sm(sa, &tmA, lead_bar, kb * kBlockK, w0 + dx, h0 + dy, n0);
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], AS ? 2 * kBTileBytes : 2 * kStageBytes);
+            if constexpr (!AS) tma_load_4d_2sm(sa, &tmA, lead_bar, kb * kBlockK, w0 + dx, h0 + dy, n0);
             if constexpr (kWide) {
               // weight rows of this CTA: its quarter of each 160-wide half (tmB's box is BN / 4 rows), so that the pair's
               // MMA h sees the rows [h * 160, h * 160 + 160) of the tile in order
@@ -534,6 +572,15 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             phase ^= 1;
           }
         }
+        if constexpr (AS) {
+          // the M switch is the one place where this mode waits for DRAM: pull the NEXT M pair's rows into L2 meanwhile
+          if (ntile == 0 && p.as_prefetch && plocal + n_tiles < n_local) {
+            const int mt1 = (tile_of(plocal + n_tiles) / n_tiles) * CS + crank;
+            const int w1 = (mt1 % p.tiles_w) * p.bw, h1 = ((mt1 / p.tiles_w) % p.tiles_h) * p.bh;
+            const int n1 = mt1 < p.tiles_w * p.tiles_h * p.tiles_g ? (mt1 / (p.tiles_w * p.tiles_h)) * p.bn : p.NI;
+            for (int kb = 0; kb < p.kblocks; ++kb) tma_prefetch_l2_4d(&tmA, kb * kBlockK, w1, h1, n1);
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -542,15 +589,19 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       constexpr uint32_t idesc = umma_idesc_f16(TWO ? 2 * kBlockM : kBlockM, kWide ? BN / 2 : BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      int local = 0;
       if (ws) mbar_wait(b_full, 0);
-      for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++local) {
+      for (int local = 0; local < n_local; ++local) {
+        const int as_j = AS ? local / n_tiles : 0;          // AS: M pair index of this cluster, N tile inside it
+        const int as_nt = AS ? local - as_j * n_tiles : 0;
         const int buf = acc_buf(local);
         mbar_wait(&tmem_empty_bar[buf], acc_phase(local) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
         stamp(local, 2);
         const uint32_t tacc = tmem_base + buf * kAccStride;
         for (int it = 0; it < its_per_tile; ++it) {
+          if constexpr (AS) {
+            if (as_nt == 0) mbar_wait(&a_full[it], (uint32_t)(as_j & 1));  // resident activation slice of this M pair
+          }
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = ws ? smem_u32(a_ring + stage * kABytes) : smem_u32(smem + stage * kStageBytes);
@@ -570,7 +621,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
             }
             continue;
           }
-          const uint64_t adesc = umma_desc_kmajor_sw128(sa);
+          const uint64_t adesc = umma_desc_kmajor_sw128(AS ? smem_u32(smem + it * kStageBytes) : sa);
           const uint64_t bdesc = umma_desc_kmajor_sw128(ws ? smem_u32(b_res + it * (BN * 128)) : sa + kABytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
@@ -588,6 +639,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           if constexpr (TWO) umma_commit_2sm(&empty_bar[stage], kMask);
           else if constexpr (CS > 1) umma_commit_multicast(&empty_bar[stage], kMask);
           else umma_commit(&empty_bar[stage]);
+          if constexpr (AS) {
+            if (as_nt == n_tiles - 1) umma_commit_2sm(&a_empty[it], kMask);  // last reader of the slice: it may be replaced
+          }
           if (++stage == nstages) {
             stage = 0;
             phase ^= 1;
@@ -617,7 +671,6 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     const bool has_res = !GEGLU && p.residual != nullptr && p.dbg_skip != 4;  // dbg_skip 4: residual term dropped
     const int my_chunks = (NCHUNK - g + 1) / 2;  // chunks g, g+2, ...
     uint32_t res_phase = 0;
-    int local = 0;
     // DS: request the residual tile of `tile_` into staging slab `slab_` (barrier index 2 * slab_ + g)
     auto request_res = [&](int tile_, int slab_) {
       const int ntile_ = tile_ % n_tiles;
@@ -630,7 +683,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                     ntile_ * OUT_W + chunk * CW, w0_, h0_, n0_);
     };
     if constexpr (DS) {
-      if (issuer && has_res && my_chunks > 0 && tile_first < total_tiles) request_res(tile_first, 0);
+      if (issuer && has_res && my_chunks > 0 && n_local > 0) request_res(tile_of(0), 0);
     }
     // GEGLU: the hidden | gate bias slices of a tile's chunks are staged in shared memory one tile ahead (threads r < 16 of
     // each group: one 16-byte vector each, requested at the top of the previous tile and written at its end, so the L2
@@ -651,14 +704,15 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       return reinterpret_cast<uint4*>(gb_base + ((buf_ * 2 + g) * 2 + (r >> 3)) * 64) + (r & 7);
     };
     if constexpr (GEGLU) {
-      if (r < 16 && tile_first < total_tiles) *gbias_slot(0) = gbias_fetch(tile_first);  // visible after the tile's top barrier
+      if (r < 16 && n_local > 0) *gbias_slot(0) = gbias_fetch(tile_of(0));  // visible after the tile's top barrier
     }
-    for (int tile = tile_first; tile < total_tiles; tile += tile_step, ++local) {
+    for (int local = 0; local < n_local; ++local) {
+      const int tile = tile_of(local);
       uint8_t* const slab = staging + (DS ? (local & 1) * kStagingBytes : 0);
       uint4 gb_next = make_uint4(0u, 0u, 0u, 0u);
-      const bool gb_pre = GEGLU && r < 16 && tile + tile_step < total_tiles;
+      const bool gb_pre = GEGLU && r < 16 && local + 1 < n_local;
       if constexpr (GEGLU) {
-        if (gb_pre) gb_next = gbias_fetch(tile + tile_step);
+        if (gb_pre) gb_next = gbias_fetch(tile_of(local + 1));
       }
       const int ntile = tile % n_tiles;
       const int mtile = (tile / n_tiles) * CS + crank;
@@ -881,7 +935,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           // residual into it; it has the rest of this tile (two chunks, barrier, store, loop turn) to land
           if (chunk == g && issuer && has_res) {
             bulk_wait_group_read<0>();
-            if (tile + tile_step < total_tiles) request_res(tile + tile_step, (local + 1) & 1);
+            if (local + 1 < n_local) request_res(tile_of(local + 1), (local + 1) & 1);
           }
         }
         if constexpr (!TILEWIDE) {
@@ -962,7 +1016,7 @@ constexpr int kP2TileVecBytes = 2 * 3 * kP2BN * 2;          // folded LayerNorm:
 template <int STAGES, bool WS>
 constexpr int pair160_smem_bytes() {
   return (WS ? STAGES * kABytes + kP2WsKBlocks * kP2BTileBytes : STAGES * kP2StageBytes) + 2 * kP2SlabBytes +
-         kP2BiasBytes + kP2RowStatBytes + kP2TileVecBytes + 256;
+         kP2BiasBytes + kP2RowStatBytes + kP2TileVecBytes + 384;
 }
 
 // WS (weight-stationary, K <= 320): these GEMMs are bound by what the SM can pull through TMA (knock-outs in
@@ -985,7 +1039,16 @@ constexpr int pair160_smem_bytes() {
 // (QKV 73728x320->960 59.3 -> 65.1 us, 18432x640->1920 50.9 -> 56.2, 4608x1280->3840 43.9 -> 50.7): 24 % fewer bytes
 // out of L2 buy nothing, the time follows the number of SMs at work (132 / 148). So the L2 -> SM throughput is NOT what
 // bounds these GEMMs; what a CTA pair can keep in flight is (the ring-latency law). Opt-in.
-template <int STAGES, bool WS, int CL = 2>
+//
+// AS (activation-stationary, K <= 320, >= 3 N tiles): with K = 320 a tile needs all five stages of the ring, so stage s of
+// tile i + 1 can only be requested when the MMAs of stage s of tile i have retired, and every tile pays a full load round
+// trip (~4 000 clk under load against 1 600 clk of MMAs: the ring-latency law). The weight-stationary mode above does not
+// change that (the activation stream still needs the whole ring per tile), which is why it measured equal. Here a cluster
+// takes ALL N tiles of an M pair: the pair's 2 x 128 activation rows (5 x 16 KB per CTA, the activation parts of the five
+// stages) are loaded once per M pair and stay put, and only the weight half-tiles (10 KB per K block, L2-resident) cycle
+// through the five weight parts of the stages. Operand bytes per tile drop from 2 x 130 KB to 2 x 50 KB, the activation
+// is read exactly once (no reliance on L2 for the re-reads), and the weight ring holds a whole tile ahead.
+template <int STAGES, bool WS, int CL = 2, bool AS = false>
 __global__ void __launch_bounds__(kP2Threads, 1)
 gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
@@ -993,6 +1056,7 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   static_assert(CL == 2 || (CL == 4 && !WS), "cluster of one pair, or of two pairs sharing the activation rows");
+  static_assert(!AS || (!WS && CL == 2), "activation-stationary mode: plain pair clusters");
   constexpr bool C4 = CL == 4;
   constexpr uint32_t kAccStride = 256;  // TMEM columns per accumulator buffer
   constexpr int kOperandBytes = WS ? STAGES * kABytes + kP2WsKBlocks * kP2BTileBytes : STAGES * kP2StageBytes;
@@ -1012,7 +1076,9 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   uint64_t* b_full = res_full + 2;               // WS: resident weights landed (leader counts both CTAs' bytes)
   uint64_t* b_free = b_full + 1;                 // WS: every MMA that read the resident weights has completed
   uint64_t* stat_full = b_free + 1;              // [2] folded LayerNorm: the row statistics of the tile are in smr
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(stat_full + 2);
+  uint64_t* a_full = stat_full + 2;              // AS [5]: resident activation slice landed (leader counts both CTAs' bytes)
+  uint64_t* a_empty = a_full + 5;                // AS [5]: the last N tile of the M pair has read the slice
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_empty + 5);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1027,9 +1093,11 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int groups = total_tiles / n_tiles;  // M-tile pairs
   // units of this pair: WS -> contiguous range of the N-major order; else round robin over the M-major order (CL = 4:
   // the cluster takes units 2s and 2s + 1 -- same rows, adjacent N tiles, n_tiles is even -- one per pair)
-  const int u_begin = WS ? (int)((long long)cid * total_tiles / n_clusters) : C4 ? 2 * cid + pair_id : cid;
-  const int u_end = WS ? (int)((long long)(cid + 1) * total_tiles / n_clusters) : total_tiles;
-  const int u_step = WS ? 1 : C4 ? 2 * n_clusters : n_clusters;
+  // AS: the cluster's units are numbered locally: unit u = (its j-th M pair = cid + j * n_clusters, N tile u % n_tiles)
+  const int as_pairs = AS && cid < groups ? (groups - cid + n_clusters - 1) / n_clusters : 0;
+  const int u_begin = WS ? (int)((long long)cid * total_tiles / n_clusters) : AS ? 0 : C4 ? 2 * cid + pair_id : cid;
+  const int u_end = WS ? (int)((long long)(cid + 1) * total_tiles / n_clusters) : AS ? as_pairs * n_tiles : total_tiles;
+  const int u_step = (WS || AS) ? 1 : C4 ? 2 * n_clusters : n_clusters;
   const int its_per_tile = p.taps * p.kblocks;
   const bool has_res = p.residual != nullptr && p.dbg_skip != 4;  // dbg_skip 4 (tuning): residual term dropped
   // tuning trace (tools/gemm_trace.py): CTA 0, per tile: 0-1 producer (first / last load issued), 2-3 MMA thread
@@ -1060,6 +1128,10 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     mbar_init(b_free, 1);
     mbar_init(&stat_full[0], 1);
     mbar_init(&stat_full[1], 1);
+    for (int s = 0; s < 5; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2sm<2 * kAccStride>(tmem_ptr);
@@ -1074,6 +1146,10 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (WS) {
       ntile = u / groups;
       mg = u - ntile * groups;
+    } else if (AS) {
+      const int j = u / n_tiles;
+      ntile = u - j * n_tiles;
+      mg = cid + j * n_clusters;
     } else {
       ntile = u % n_tiles;
       mg = u / n_tiles;
@@ -1130,9 +1206,22 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             dy = tap / p.tap_w - (p.tap_h >> 1);
             dx = tap % p.tap_w - (p.tap_w >> 1);
           }
+          if constexpr (AS) {
+            if (ntile == 0) {  // first N tile of an M pair: (re)load the resident activation slice of this K block
+              const int j = u / n_tiles;
+              mbar_wait(&a_empty[it], (uint32_t)(j & 1) ^ 1u);
+              const uint32_t lead_a = mapa_shared(smem_u32(&a_full[it]), lead_rank);
+              if (crank == 0) mbar_expect_tx(&a_full[it], 2 * kABytes);
+              tma_load_4d_2sm(smem + it * kP2StageBytes, &tmA, lead_a, kb * kBlockK, w0 + dx, h0 + dy, n0);
+            }
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           const uint32_t lead_bar = mapa_shared(smem_u32(&full_bar[stage]), lead_rank);
-          if constexpr (WS) {
+          if constexpr (AS) {
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * kP2BTileBytes);
+            tma_load_3d_2sm(smem + stage * kP2StageBytes + kABytes, &tmB, lead_bar, kb * kBlockK,
+                            ntile * kP2BN + crank * (kP2BN / 2), tap);
+          } else if constexpr (WS) {
             if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * kABytes);
             tma_load_4d_2sm(smem + stage * kABytes, &tmA, lead_bar, kb * kBlockK, w0 + dx, h0 + dy, n0);
           } else {
@@ -1151,6 +1240,15 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
+          }
+        }
+        if constexpr (AS) {
+          // the M switch is the one place where this mode waits for DRAM (trace: ~5 900 clk against ~3 100 per tile): pull the
+          // NEXT M pair's rows into L2 while this one is being worked on
+          if (ntile == 0 && p.as_prefetch && mg + n_clusters < groups) {
+            int w1, h1, n1;
+            origin(mg + n_clusters, w1, h1, n1);
+            for (int kb = 0; kb < p.kblocks; ++kb) tma_prefetch_l2_4d(&tmA, kb * kBlockK, w1, h1, n1);
           }
         }
       }
@@ -1175,15 +1273,22 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             cur_nt = ntile;
           }
         }
+        const int as_j = AS ? u / n_tiles : 0;           // AS: M pair index of this cluster, N tile inside it
+        const int as_nt = AS ? u - as_j * n_tiles : 0;
         mbar_wait(&tmem_empty_bar[buf], ((local >> 1) & 1) ^ 1);  // both CTAs' epilogue warps have read this buffer
         tc_fence_after();
         stamp(local, 2);
         const uint32_t tacc = tmem_base + buf * kAccStride;
         for (int it = 0; it < its_per_tile; ++it) {
+          if constexpr (AS) {
+            if (as_nt == 0) mbar_wait(&a_full[it], (uint32_t)(as_j & 1));  // resident activation slice of this M pair
+          }
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (it == 0) stamp(local, 13);                      // first / last operand stage of the tile seen
+          if (it == its_per_tile - 1) stamp(local, 14);
           const uint32_t sa = smem_u32(smem + stage * (WS ? kABytes : kP2StageBytes));
-          const uint64_t adesc = umma_desc_kmajor_sw128(sa);
+          const uint64_t adesc = umma_desc_kmajor_sw128(AS ? smem_u32(smem + it * kP2StageBytes) : sa);
           const uint64_t bdesc = umma_desc_kmajor_sw128(WS ? smem_u32(b_res + it * kP2BTileBytes) : sa + kABytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
@@ -1191,6 +1296,9 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             umma_f16_ss_2sm(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
           }
           umma_commit_2sm(&empty_bar[stage], kAllMask);
+          if constexpr (AS) {
+            if (as_nt == n_tiles - 1) umma_commit_2sm(&a_empty[it], kMask);  // last reader of the slice: it may be replaced
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -1372,6 +1480,11 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           mg = 0;
           ++ntile;
         }
+      } else if constexpr (AS) {
+        if (++ntile == n_tiles) {
+          ntile = 0;
+          mg += n_clusters;
+        }
       } else {
         ntile += step_n;
         mg += step_m;
@@ -1520,13 +1633,13 @@ static int sm_count() {  // of the current device (cached per device ordinal)
 }
 
 template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, int CS, bool TWO = false, bool HALO = false,
-          bool DS = false>
+          bool DS = false, bool AS = false>
 static int launch_persistent_cs(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmD,
                                 const CUtensorMap& tmR, const GemmKParams& kp, int m_tiles, int n_tiles,
                                 cudaStream_t stream) {
   constexpr int smem = persist_smem_bytes<BN, STAGES, CW, GEGLU, TILEWIDE, TWO, HALO, DS>();
   static_assert(smem <= 227 * 1024, "persistent GEMM configuration exceeds shared memory");
-  auto kern = gemm_tc_persistent_kernel<BN, STAGES, CW, GEGLU, TILEWIDE, CS, TWO, HALO, DS>;
+  auto kern = gemm_tc_persistent_kernel<BN, STAGES, CW, GEGLU, TILEWIDE, CS, TWO, HALO, DS, AS>;
   static DeviceOnce configured;
   if (configured.first()) {
     IVV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -1534,7 +1647,7 @@ static int launch_persistent_cs(const CUtensorMap& tmA, const CUtensorMap& tmB, 
   const int groups = (m_tiles + CS - 1) / CS;
   const int total = groups * n_tiles;  // (super) tiles
   int clusters = sm_count() / CS;
-  if (clusters > total) clusters = total;
+  if (clusters > (AS ? groups : total)) clusters = AS ? groups : total;  // AS: a cluster owns whole M pairs
   if (kp.ws_stages > 0) clusters = (sm_count() / n_tiles) * n_tiles;  // weight-stationary: one N tile per CTA
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(clusters * CS));
@@ -1561,18 +1674,18 @@ static int launch_persistent_cs(const CUtensorMap& tmA, const CUtensorMap& tmB, 
   return 0;
 }
 
-template <int STAGES, bool WS>
+template <int STAGES, bool WS, bool AS = false>
 static int launch_pair160(const CUtensorMap& tmA, const CUtensorMap& tmB2, const CUtensorMap& tmD, const CUtensorMap& tmR,
                           const GemmKParams& kp, int m_tiles, int n_tiles, cudaStream_t stream) {
   constexpr int smem = pair160_smem_bytes<STAGES, WS>();
   static_assert(smem <= 227 * 1024, "pair160 configuration exceeds shared memory");
-  auto kern = gemm_tc_pair160_kernel<STAGES, WS>;
+  auto kern = gemm_tc_pair160_kernel<STAGES, WS, 2, AS>;
   static DeviceOnce configured;
   if (configured.first()) IVV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int groups = (m_tiles + 1) / 2;
   const int total = groups * n_tiles;
   int clusters = sm_count() / 2;
-  if (clusters > total) clusters = total;
+  if (clusters > (AS ? groups : total)) clusters = AS ? groups : total;  // AS: a cluster owns whole M pairs
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(clusters * 2));
   cfg.blockDim = dim3(kP2Threads);
@@ -1698,7 +1811,7 @@ namespace ivv {
 // -1 = unset. IVV_HALO / IVV_DS / IVV_EPI2 / IVV_PAIR: 0 disables; IVV_CLUSTER=2, IVV_FORCE_BN=32|64|128|160|256,
 // IVV_NO_WS=1, IVV_DEBUG_SKIP=1..5 (knock-outs, results are garbage).
 struct GemmEnv {
-  int halo, ds, epi2, pair, cluster, force_bn, no_ws, ws, dbg_skip, geglu_ds, cl4, cl4_min, wide;
+  int halo, ds, epi2, pair, cluster, force_bn, no_ws, ws, dbg_skip, geglu_ds, cl4, cl4_min, wide, as, as_pf;
 };
 static const GemmEnv& gemm_env() {
   static const GemmEnv e = [] {
@@ -1720,6 +1833,8 @@ static const GemmEnv& gemm_env() {
     g.cl4 = geti("IVV_CL4");
     g.cl4_min = geti("IVV_CL4_MIN");
     g.wide = geti("IVV_WIDE");
+    g.as = geti("IVV_AS");
+    g.as_pf = geti("IVV_AS_PF");
     return g;
   }();
   return e;
@@ -1751,8 +1866,10 @@ extern "C" int ivv_debug_conv_box(int64_t w, int64_t h, int64_t n_img, int32_t w
 extern "C" int ivv_debug_cl4_clusters() { return ivv::pair160_cl4_clusters<5>(); }
 
 // tuning / test hook (not in ivv.h): tile width (BLOCK_N) the calling thread's last ivv_gemm chose
-static thread_local int g_last_bn = 0;
+static thread_local int g_last_bn = 0, g_last_as = 0;
 extern "C" int ivv_debug_last_gemm_tile() { return g_last_bn; }
+// 1 if the calling thread's last ivv_gemm ran the activation-stationary mode of the short-K pair kernel
+extern "C" int ivv_debug_last_gemm_as() { return g_last_as; }
 
 static long long* g_gemm_trace = nullptr;
 // tuning only: clock64 trace of CTA 0 of the next persistent-kernel launches into buf ([32 tiles][16] int64); NULL = off
@@ -1787,6 +1904,7 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
   choose_box(a->w, a->h, a->n_img, want_halo, &kp.bw, &kp.bh, &kp.bn);
   kp.halo_bytes = (kp.bh + 2) * kp.bw * 128;
   kp.trace = g_gemm_trace;
+  kp.as_prefetch = env.as_pf != 0;  // IVV_AS_PF=0: no L2 prefetch of the next M pair in the activation-stationary modes
   kp.tiles_w = (int)((a->w + kp.bw - 1) / kp.bw);
   kp.tiles_h = (int)((a->h + kp.bh - 1) / kp.bh);
   kp.tiles_g = (int)((a->n_img + kp.bn - 1) / kp.bn);
@@ -1918,6 +2036,7 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
   }
   const int n_tiles = (int)((a->n_out + bn_sel - 1) / bn_sel);
   g_last_bn = bn_sel;
+  g_last_as = 0;
 
   // ---- tensor maps ----
   CUtensorMap tmA, tmB, tmB2;
@@ -2001,6 +2120,13 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
       // (profiles/r02_gemm_pair160_ncu.txt), so it is opt-in: IVV_WS=1.
       if (a->taps == 1 && kp.kblocks <= kP2WsKBlocks && env.ws == 1)
         return launch_pair160<5, true>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
+      // Activation-stationary mode (see the kernel): K <= 320 with at least three N tiles and enough M pairs for every
+      // cluster (the 320 -> 960 QKV projections of the 32x48 level). IVV_AS=0 disables, IVV_AS=2 takes it from two N tiles.
+      if (a->taps == 1 && kp.kblocks <= 5 && n_tiles >= (env.as == 2 ? 2 : 3) && (m_tiles + 1) / 2 >= sm_count() / 2 &&
+          env.as != 0) {
+        g_last_as = 1;
+        return launch_pair160<5, false, true>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
+      }
       return launch_pair160<5, false>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
     }
     if (ds) {
@@ -2027,6 +2153,13 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
         // short main loops (K <= 320: the 32x48 level): the epilogue sets the pace, so spend one pipeline stage on a second
         // output slab -- the store of tile i drains while tile i+1 is written. IVV_GEGLU_DS=0 disables, =2 takes it for
         // every K (tuning hooks).
+        // ... and keep the activation rows of an M pair resident while the cluster walks its N tiles (AS, see the kernel):
+        // the 320 -> 2560 GEGLU projection of the 32x48 level. IVV_AS=0 disables.
+        if (env.geglu_ds != 0 && kp.taps * kp.kblocks <= 5 && n_tiles >= 3 && (m_tiles + 1) / 2 >= sm_count() / 2 &&
+            env.as != 0) {
+          g_last_as = 1;
+          return launch_persistent_cs<256, 5, 32, true, true, 2, true, false, true, true>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
+        }
         if (env.geglu_ds != 0 && (kp.taps * kp.kblocks <= 5 || env.geglu_ds == 2))
           return launch_persistent_cs<256, 5, 32, true, true, 2, true, false, true>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
         IVV_PAIR_LAUNCH(256, 6, 32, true, true);

@@ -108,7 +108,36 @@ def test_linear_pair160_variants(rows, k, n, bias, res, relu):
     assert torch.equal(out2, out.contiguous())
 
 
-@pytest.mark.parametrize("rows,c,n,frames,hw", [(4608, 320, 960, 0, 0), (1000, 640, 640, 0, 0), (1152, 1280, 3840, 0, 0),
+@pytest.mark.parametrize("rows,k,n,bias,res,relu", [
+    (73728, 320, 960, False, False, False),        # the QKV projection of the 32x48 level
+    (128 * 301 + 50, 320, 960, True, True, False),  # ragged last M tile, odd number of M tiles (ghost tile of the last pair)
+    (40000, 320, 480, True, False, True), (30000, 200, 480, False, True, False),  # three N tiles; K tail (200 = 3 * 64 + 8)
+    (40000, 256, 1600, True, True, False)])
+def test_linear_activation_stationary(rows, k, n, bias, res, relu):
+    """Short-K pair kernel, activation-stationary mode (K <= 320, >= 3 N tiles, >= 74 M pairs): a cluster keeps the 2 x 128
+    activation rows of an M pair in shared memory and walks all its N tiles; only weight tiles stream."""
+    from insv2v_b200 import lib
+    ops = _ops()
+    x = h16(rows, k, seed=1)
+    w = h16(n, k, scale=k ** -0.5, seed=2)
+    b = h16(n, seed=3) if bias else None
+    r = h16(rows, n, seed=4) if res else None
+    out = ops.gemm(x, ops.pack_linear(w), n_img=1, h=1, w=rows, c=k, bias=b, residual=r, relu=relu)
+    assert lib.load().ivv_debug_last_gemm_as() == 1
+    ref = x.float() @ w.float().t()
+    if bias:
+        ref = ref + b.float()
+    if res:
+        ref = ref + r.float()
+    if relu:
+        ref = ref.clamp_min(0)
+    report(f"AS {rows}x{k}x{n} bias={bias} res={res} relu={relu}", out, ref)
+    out2 = ops.gemm(x, ops.pack_linear(w), n_img=1, h=1, w=rows, c=k, bias=b, residual=r, relu=relu)
+    assert torch.equal(out2, out)
+
+
+@pytest.mark.parametrize("rows,c,n,frames,hw", [(4608, 320, 960, 0, 0), (20000, 320, 960, 0, 0),
+                                              (3 * 16 * 512, 320, 960, 16, 512),  # activation-stationary consumers (1000, 640, 640, 0, 0), (1152, 1280, 3840, 0, 0),
                                               (2 * 5 * 384, 320, 960, 5, 384), (3 * 16 * 128, 640, 1920, 16, 128)])
 def test_layernorm_folded_into_gemms(rows, c, n, frames, hw):
     """K8 fold: the producer GEMM emits per-row partial statistics of its output y, the consumer GEMM computes
@@ -154,7 +183,11 @@ def test_layernorm_folded_into_gemms(rows, c, n, frames, hw):
 
 
 @pytest.mark.parametrize("rows,c,mult,bias", [(500, 320, 8, True), (40000, 320, 8, True), (40000, 320, 8, False),
-                                              (9100, 640, 8, True), (2400, 1280, 4, True)])
+                                              (9100, 640, 8, True), (2400, 1280, 4, True),
+                                              # activation-stationary mode (K <= 320, >= 74 M pairs): ragged and ghost tiles,
+                                              # the full-size call, a K tail (72 = 64 + 8), three N tiles
+                                              (128 * 301 + 50, 320, 8, True), (73728, 320, 8, True), (30000, 72, 32, True),
+                                              (25000, 192, 4, False)])
 def test_linear_geglu(rows, c, mult, bias):
     """GEGLU epilogue (hidden * gelu(gate), tile-interleaved weights). The larger cases give every cluster a run of
     tiles: the bias slices staged one tile ahead in shared memory and the two alternating output slabs (K <= 320) are
@@ -165,6 +198,9 @@ def test_linear_geglu(rows, c, mult, bias):
     b = h16(mult * c, scale=0.5, seed=3) if bias else None
     wp, bp = ops.pack_geglu(w, b if bias else torch.zeros(mult * c, device="cuda", dtype=torch.float16))
     out = ops.linear(x, wp, bias=bp if bias else None, geglu=True)
+    from insv2v_b200 import lib
+    assert lib.load().ivv_debug_last_gemm_as() == int(c <= 320 and rows > 146 * 128 and mult * c >= 768)
+    assert torch.equal(out, ops.linear(x, wp, bias=bp if bias else None, geglu=True))
     y = x.float() @ w.float().t()
     if bias:
         y = y + b.float()

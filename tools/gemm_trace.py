@@ -53,7 +53,7 @@ names = ["tma:first", "tma:last", "mma:acc ok", "mma:commit", "epi:top", "epi:dr
          "epi:bar", "epi:stored", "c0:bias req", "c0:acc regs", "c0:bias add", "c0:written"]
 if os.environ.get("IVV_EPI2", "1") != "0" and n % 160 == 0 and k <= 1280:  # v3 pair kernel (gemm_tc_pair160_kernel)
     names = ["tma:first", "tma:last", "mma:acc ok", "mma:commit", "epi:top", "epi:acc", "epi:regs", "epi:slab ok",
-             "epi:written", "st:full", "st:issued", "st:drained", "st:res req"]
+             "epi:written", "st:full", "st:issued", "st:drained", "st:res req", "mma:stage0", "mma:stageN"]
 print(f"rows={rows} k={k} n={n} res={res} ln={int(LN)}  (SM clocks since the first stamp of CTA 0)")
 print("tile " + " ".join(f"{s:>11s}" for s in names))
 for g in range(32):
