@@ -331,7 +331,7 @@ template <int BN, int STAGES, int CW, bool GEGLU, bool TILEWIDE, bool TWO = fals
 constexpr int persist_smem_bytes() {
   // TILEWIDE: the whole fp16 output tile is staged (DS: two such slabs); otherwise one CW-wide slab per epilogue group
   return STAGES * (HALO ? kHaloBytes + 3 * (BN / 2) * 128 : kABytes + (TWO ? BN / 2 : BN) * 128) +
-         (TILEWIDE ? (DS ? 2 : 1) * kBlockM * (GEGLU ? BN / 2 : BN) * 2 : 2 * kBlockM * CW * 2) + 256 +
+         (TILEWIDE ? (DS ? 2 : 1) * kBlockM * (GEGLU ? BN / 2 : BN) * 2 : (BN > 256 ? 4 : 2) * kBlockM * CW * 2) + 256 +
          (GEGLU ? kGegluBiasBytes : 0);
 }
 
@@ -396,7 +396,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     }
   };
   constexpr int kChunkBytes = kBlockM * CW * 2;  // one [128 rows x CW fp16] swizzled slab per column chunk
-  constexpr int kStagingBytes = TILEWIDE ? kBlockM * (GEGLU ? BN / 2 : BN) * 2 : 2 * kChunkBytes;
+  constexpr int kStagingBytes = TILEWIDE ? kBlockM * (GEGLU ? BN / 2 : BN) * 2 : (kWide ? 4 : 2) * kChunkBytes;
   constexpr uint32_t kAccStride = kWide ? 0u : acc_stride_for<BN>();
   constexpr uint32_t kTmemCols = kWide ? 512u : 2 * kAccStride;
   // accumulator buffer and barrier parity of the CTA's local-th tile (WIDE: one buffer, its barriers flip every tile)
@@ -706,6 +706,11 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     if constexpr (GEGLU) {
       if (r < 16 && n_local > 0) *gbias_slot(0) = gbias_fetch(tile_of(0));  // visible after the tile's top barrier
     }
+    // WIDE: the epilogue runs in the open (one accumulator), so it is kept short: two 32-column slabs per group used
+    // alternately (only the store issued two chunks ago must have drained), and the residual comes straight from global
+    // memory into registers, one chunk ahead -- the first chunk's while the main loop is still running. (Ring staging
+    // with a TMA-fetched residual paid a store drain plus a TMA round trip per chunk: ~14 000 clk per tile.)
+    uint32_t wchunk = 0;  // chunks this group has written so far (slab parity)
     for (int local = 0; local < n_local; ++local) {
       const int tile = tile_of(local);
       uint8_t* const slab = staging + (DS ? (local & 1) * kStagingBytes : 0);
@@ -751,6 +756,15 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         if (!has_res) named_bar_sync(1 + g, 128);
       }
       if (etr) stamp(local, 5);
+      uint4 rcur[kWide ? VPR : 1], rnxt[kWide ? VPR : 1];
+      const __half* rrow = nullptr;  // WIDE: this thread's residual row (nullptr: none / row outside the tensor)
+      if constexpr (kWide) {
+        if (has_res && valid) rrow = p.residual + pix * p.res_ld + ntile * OUT_W;
+#pragma unroll
+        for (int cc = 0; cc < VPR; ++cc)
+          rcur[cc] = rrow != nullptr && g < NCHUNK ? __ldg(reinterpret_cast<const uint4*>(rrow + g * CW) + cc)
+                                                   : make_uint4(0u, 0u, 0u, 0u);
+      }
       mbar_wait(&tmem_full_bar[buf], acc_phase(local));
       tc_fence_after();
       if (etr) stamp(local, 6);
@@ -773,10 +787,19 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       }
 #pragma unroll 1
       for (int chunk = g; chunk < NCHUNK; chunk += 2) {
-        uint8_t* stg = TILEWIDE ? slab + chunk * kChunkBytes : staging + g * kChunkBytes;
+        uint8_t* stg = TILEWIDE ? slab + chunk * kChunkBytes
+                                : staging + (kWide ? 2 * g + (int)(wchunk & 1u) : g) * kChunkBytes;
         const int c0 = chunk * CW;             // column inside the tile's output window
         const int ocol0 = ntile * OUT_W + c0;  // global output column
-        if constexpr (!TILEWIDE) {
+        if constexpr (kWide) {
+          ++wchunk;
+          if (issuer) bulk_wait_group_read<1>();  // the store issued two chunks ago has left this slab
+#pragma unroll
+          for (int cc = 0; cc < VPR; ++cc)  // residual of this group's next chunk: in flight under this chunk's work
+            rnxt[cc] = rrow != nullptr && chunk + 2 < NCHUNK ? __ldg(reinterpret_cast<const uint4*>(rrow + c0 + 2 * CW) + cc)
+                                                             : make_uint4(0u, 0u, 0u, 0u);
+          named_bar_sync(1 + g, 128);
+        } else if constexpr (!TILEWIDE) {
           // ring mode: one slab per group; wait for its previous store, then fetch this chunk's residual into it
           if (issuer) {
             bulk_wait_group_read<0>();
@@ -896,7 +919,13 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         // shared-memory array, so in the per-slot form below the compiler keeps LDS(cc+1) behind STS(cc) and the pass
         // becomes four dependent LDS -> FADD -> STS groups (~490 clk per chunk in the clock64 trace).
         uint4 rpre[CW == 32 ? VPR : 1];
-        if constexpr (CW == 32) {
+        if constexpr (kWide) {
+#pragma unroll
+          for (int cc = 0; cc < VPR; ++cc) {
+            rpre[cc] = rcur[cc];
+            rcur[cc] = rnxt[cc];
+          }
+        } else if constexpr (CW == 32) {
           if (has_res) {
 #pragma unroll
             for (int cc = 0; cc < VPR; ++cc)
@@ -1811,7 +1840,7 @@ namespace ivv {
 // -1 = unset. IVV_HALO / IVV_DS / IVV_EPI2 / IVV_PAIR: 0 disables; IVV_CLUSTER=2, IVV_FORCE_BN=32|64|128|160|256,
 // IVV_NO_WS=1, IVV_DEBUG_SKIP=1..5 (knock-outs, results are garbage).
 struct GemmEnv {
-  int halo, ds, epi2, pair, cluster, force_bn, no_ws, ws, dbg_skip, geglu_ds, cl4, cl4_min, wide, as, as_pf;
+  int halo, ds, epi2, pair, cluster, force_bn, no_ws, ws, dbg_skip, geglu_ds, cl4, cl4_min, wide, wide_k, as, as_pf;
 };
 static const GemmEnv& gemm_env() {
   static const GemmEnv e = [] {
@@ -1833,6 +1862,7 @@ static const GemmEnv& gemm_env() {
     g.cl4 = geti("IVV_CL4");
     g.cl4_min = geti("IVV_CL4_MIN");
     g.wide = geti("IVV_WIDE");
+    g.wide_k = geti("IVV_WIDE_K");
     g.as = geti("IVV_AS");
     g.as_pf = geti("IVV_AS_PF");
     return g;
@@ -1983,8 +2013,8 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
   // Residual GEMMs with short main loops (the attention / temporal out-projections, K = 320 and 640): pair kernel with
   // two staging slabs and 160-wide tiles, so the residual fetch of the next tile overlaps this tile's epilogue.
   // IVV_DS=0 disables (tuning hook).
-  const bool ds = a->residual != nullptr && !halo && !a->geglu && a->taps == 1 && a->c <= 640 && (a->n_out % 160) == 0 &&
-                  persistent_ok && m_tiles >= 2 && env.ds != 0 && env.pair != 0 && env.cluster < 0 && env.force_bn < 0;
+  const bool ds0 = a->residual != nullptr && !halo && !a->geglu && a->taps == 1 && a->c <= 640 && (a->n_out % 160) == 0 &&
+                   persistent_ok && m_tiles >= 2 && env.ds != 0 && env.pair != 0 && env.cluster < 0 && env.force_bn < 0;
   // v3 pair kernel (16-warp epilogue + store warp, 160-wide tiles): every short-K GEMM whose N is a multiple of 160 and
   // that needs no per-row bias. IVV_EPI2=0 falls back to the v2 kernels (tuning hook).
   const bool is_linear = a->taps == 1 && a->h == 1 && a->n_img == 1;
@@ -1993,11 +2023,36 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
   const bool rowbias_ok = a->rowbias == nullptr ||
                           (is_linear && a->ln_stats != nullptr && (a->rowbias_group % kBlockM) == 0 &&
                            (a->rowbias_ld % 8) == 0 && (reinterpret_cast<uintptr_t>(a->rowbias) & 15) == 0);
-  const bool pair160 = pair160_shape_ok(a->n_img * a->h * a->w, (long long)a->c * a->taps, a->n_out) && !halo &&
-                       !a->geglu && rowbias_ok && persistent_ok && a->splits <= 1 && m_tiles >= 2 &&
-                       (a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0) &&
-                       env.epi2 != 0 && env.pair < 0 && env.cluster < 0 && env.force_bn < 0;
+  const bool pair160_0 = pair160_shape_ok(a->n_img * a->h * a->w, (long long)a->c * a->taps, a->n_out) && !halo &&
+                         !a->geglu && rowbias_ok && persistent_ok && a->splits <= 1 && m_tiles >= 2 &&
+                         (a->bias == nullptr || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0) &&
+                         env.epi2 != 0 && env.pair < 0 && env.cluster < 0 && env.force_bn < 0;
   const bool wants_fold = a->row_stats_out != nullptr || a->ln_stats != nullptr || a->rowbias_mod > 0;
+  // 320-wide tiles (pair kernel, two N = 160 MMAs per k-step, one accumulator): taken when the tile list then needs fewer
+  // rounds of the 74 clusters. Cost model in clocks per (tap, k-block) of a tile, calibrated on B200
+  // (profiles/r02_gemm_wide_ab.txt): 950 for the 320-wide tile, 840 / 772 for 256 / 160 (700 in the short-K pair kernel);
+  // the 320-wide tile also pays its epilogue in the open (one accumulator): ~4 000 clk.
+  // The N = 1280 convolutions and projections of the 8x12 level: 72 tiles = one round instead of 144 = two; the FF
+  // out-projection of the 16x24 level: two rounds instead of three (measured equal). From K = 2560: with K = 1280 the wide tile
+  // LOSES against the short-K pair kernel (73728x1280->320 72.2 -> 75.1 us, 4608x1280->1280 20.2 -> 22.5 us,
+  // profiles/r02_gemm_wide_ab.txt): twenty k-blocks do not amortise an epilogue in the open. IVV_WIDE=0 disables,
+  // IVV_WIDE_K=<k> sets the shortest K, IVV_FORCE_BN=320 takes it wherever it is legal (tuning hooks).
+  bool use_wide = false;
+  if (!a->geglu && !halo && !wants_fold && persistent_ok && res_ok && m_tiles >= 2 && (a->n_out % 320) == 0 &&
+      (long long)a->c * a->taps >= (env.force_bn == 320 || env.wide_k <= 0 ? 2560 : env.wide_k) && a->splits <= 1 &&
+      env.pair < 0 && env.cluster < 0 && env.no_ws < 0 && (env.force_bn < 0 || env.force_bn == 320) && env.wide != 0) {
+    const long long clusters = sm_count() / 2, pairs = (m_tiles + 1) / 2;
+    const double its = (double)kp.taps * kp.kblocks;
+    const bool alt160 = ds0 || pair160_0;
+    auto cost = [&](int bn) {
+      const long long nt = (a->n_out + bn - 1) / bn;
+      const long long rounds = (pairs * nt + clusters - 1) / clusters;
+      const double per_it = bn == 320 ? 950.0 : bn == 256 ? 840.0 : bn == 160 ? (alt160 ? 700.0 : 772.0) : 700.0;
+      return (double)rounds * (its * per_it + (bn == 320 ? 4000.0 : 0.0));
+    };
+    use_wide = env.force_bn == 320 || cost(320) < 0.95 * cost(alt160 ? 160 : bn_sel);
+  }
+  const bool ds = ds0 && !use_wide, pair160 = pair160_0 && !use_wide;
   IVV_REQUIRE(!wants_fold || (pair160 && is_linear),
               "ivv_gemm: row_stats_out / ln_stats / rowbias_mod need a linear layer served by the short-K pair kernel "
               "(ivv_gemm_ln_fold_ok(rows, k, n_out)); got rows=%lld k=%lld n_out=%lld taps=%d",
@@ -2015,25 +2070,7 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
   kp.ln_eps = a->ln_eps;
   kp.ln_inv_c = 1.f / (float)a->c;
   if (ds || pair160) bn_sel = 160;
-  // 320-wide tiles (pair kernel, two N = 160 MMAs per k-step, one accumulator): taken when the tile list then needs fewer
-  // rounds of the 74 clusters. Cost model in clocks per (tap, k-block) of a tile, calibrated on B200
-  // (profiles/r02_gemm_wide_ab.txt): 950 for the 320-wide tile, 840 / 772 for 256 / 160; the 320-wide tile also pays its
-  // epilogue in the open (one accumulator): ~7 000 clk, ~14 000 with a residual (fetched chunk by chunk).
-  // The N = 1280 convolutions and the FF out-projection of the 8x12 level: 72 tiles = one round instead of 144 = two.
-  // IVV_WIDE=0 disables, IVV_FORCE_BN=320 takes it wherever it is legal (tuning hooks).
-  if (!a->geglu && !halo && !ds && !pair160 && persistent_ok && m_tiles >= 2 && (a->n_out % 320) == 0 &&
-      (long long)a->c * a->taps >= 2560 && a->splits <= 1 && env.pair < 0 && env.cluster < 0 && env.no_ws < 0 &&
-      (env.force_bn < 0 || env.force_bn == 320) && env.wide != 0) {
-    const long long clusters = sm_count() / 2, pairs = (m_tiles + 1) / 2;
-    const double its = (double)kp.taps * kp.kblocks;
-    auto cost = [&](int bn) {
-      const long long nt = (a->n_out + bn - 1) / bn;
-      const long long rounds = (pairs * nt + clusters - 1) / clusters;
-      const double per_it = bn == 320 ? 950.0 : bn == 256 ? 840.0 : bn == 160 ? 772.0 : 700.0;
-      return (double)rounds * (its * per_it + (bn == 320 ? (a->residual ? 14000.0 : 7000.0) : 0.0));
-    };
-    if (env.force_bn == 320 || cost(320) < 0.95 * cost(bn_sel)) bn_sel = 320;
-  }
+  if (use_wide) bn_sel = 320;
   const int n_tiles = (int)((a->n_out + bn_sel - 1) / bn_sel);
   g_last_bn = bn_sel;
   g_last_as = 0;

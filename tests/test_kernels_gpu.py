@@ -661,15 +661,21 @@ def test_conv3x3_wide_tiles(n, ci, co, h, w, fused):
     assert torch.equal(out, out2)
 
 
-def test_linear_wide_tiles():
-    """FF out-projection of the 8x12 level (4608 x 5120 -> 1280 + residual): 320-wide tiles, one round."""
+@pytest.mark.parametrize("rows,k,n,res", [(4608, 5120, 1280, True), (18432, 2560, 640, True), (4608, 2560, 1280, False),
+                                          (128 * 35 + 50, 2624, 1280, True)])
+def test_linear_wide_tiles(rows, k, n, res):
+    """FF out-projections (4608 x 5120 -> 1280, 18432 x 2560 -> 640, + residual) and the 1x1 shortcuts of the 8x12 level:
+    320-wide tiles whenever they save rounds of the 74 clusters. Residual read straight from global memory one chunk
+    ahead; ragged last tile (36 M tiles, the last one with 50 rows)."""
     from insv2v_b200 import lib
     ops = _ops()
-    rows, k, n = 4608, 5120, 1280
-    x, w, b, res = h16(rows, k, seed=1), h16(n, k, scale=k ** -0.5, seed=2), h16(n, seed=3), h16(rows, n, seed=4)
-    out = ops.linear(x, ops.pack_linear(w), bias=b, residual=res)
+    x, w, b = h16(rows, k, seed=1), h16(n, k, scale=k ** -0.5, seed=2), h16(n, seed=3)
+    r = h16(rows, n, seed=4) if res else None
+    out = ops.linear(x, ops.pack_linear(w), bias=b, residual=r)
     assert lib.load().ivv_debug_last_gemm_tile() == 320
-    report("linear wide 4608x5120x1280", out, x.double() @ w.double().t() + b.double() + res.double())
+    ref = x.double() @ w.double().t() + b.double() + (r.double() if res else 0)
+    report(f"linear wide {rows}x{k}x{n}", out, ref)
+    assert torch.equal(out, ops.linear(x, ops.pack_linear(w), bias=b, residual=r))
 
 
 _WIDE_SNIPPET = r"""
