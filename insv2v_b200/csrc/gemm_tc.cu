@@ -1042,9 +1042,9 @@ constexpr int kP2StageBytes = kABytes + kP2BTileBytes;      // 16 KB activations
 constexpr int kP2WsKBlocks = 5;                             // weight-stationary mode: K <= 320
 constexpr int kP2RowStatBytes = 2 * kBlockM * 8;            // folded LayerNorm: (rstd, -mean * rstd) per row, 2 buffers
 constexpr int kP2TileVecBytes = 2 * 3 * kP2BN * 2;          // folded LayerNorm: bias | row bias | wsum slices of the tile
-template <int STAGES, bool WS>
+template <int STAGES, bool WS, int SLABS = 2>
 constexpr int pair160_smem_bytes() {
-  return (WS ? STAGES * kABytes + kP2WsKBlocks * kP2BTileBytes : STAGES * kP2StageBytes) + 2 * kP2SlabBytes +
+  return (WS ? STAGES * kABytes + kP2WsKBlocks * kP2BTileBytes : STAGES * kP2StageBytes) + SLABS * kP2SlabBytes +
          kP2BiasBytes + kP2RowStatBytes + kP2TileVecBytes + 384;
 }
 
@@ -1077,7 +1077,13 @@ constexpr int pair160_smem_bytes() {
 // stages) are loaded once per M pair and stay put, and only the weight half-tiles (10 KB per K block, L2-resident) cycle
 // through the five weight parts of the stages. Operand bytes per tile drop from 2 x 130 KB to 2 x 50 KB, the activation
 // is read exactly once (no reliance on L2 for the re-reads), and the weight ring holds a whole tile ahead.
-template <int STAGES, bool WS, int CL = 2, bool AS = false>
+//
+// SLABS = 1 (K >= 640): these GEMMs are paced by bytes in flight / load round trip (the ring-latency law), and a tile lasts
+// two or four ring revolutions while a slab is only occupied for ~3 250 clk (written, stored, drained): ONE output slab is
+// enough and the 40 KB it frees hold a sixth pipeline stage (+20 % bytes in flight). The slab-state barriers keep
+// alternating with the tile parity (slab_full / slab_free / res_full [local & 1]); only the memory is shared, so the slab
+// of tile i + 1 (residual fetch or "free") is released when the store of tile i has drained, not of tile i - 1.
+template <int STAGES, bool WS, int CL = 2, bool AS = false, int SLABS = 2>
 __global__ void __launch_bounds__(kP2Threads, 1)
 gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
@@ -1086,15 +1092,17 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   static_assert(CL == 2 || (CL == 4 && !WS), "cluster of one pair, or of two pairs sharing the activation rows");
   static_assert(!AS || (!WS && CL == 2), "activation-stationary mode: plain pair clusters");
+  static_assert(SLABS == 2 || (SLABS == 1 && !WS && !AS && CL == 2), "single output slab: plain pair clusters");
+  static_assert(STAGES <= 6, "barrier block holds six stages");
   constexpr bool C4 = CL == 4;
   constexpr uint32_t kAccStride = 256;  // TMEM columns per accumulator buffer
   constexpr int kOperandBytes = WS ? STAGES * kABytes + kP2WsKBlocks * kP2BTileBytes : STAGES * kP2StageBytes;
   uint8_t* b_res = smem + STAGES * kABytes;  // WS only: [k block][80 weight rows x 128 B]
   uint8_t* slabs = smem + kOperandBytes;
-  __half* sbias = reinterpret_cast<__half*>(slabs + 2 * kP2SlabBytes);
-  float2* smr = reinterpret_cast<float2*>(slabs + 2 * kP2SlabBytes + kP2BiasBytes);  // [2][128] (rstd, -mean * rstd)
-  __half* tvec = reinterpret_cast<__half*>(slabs + 2 * kP2SlabBytes + kP2BiasBytes + kP2RowStatBytes);  // [2][3][160]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(slabs + 2 * kP2SlabBytes + kP2BiasBytes + kP2RowStatBytes +
+  __half* sbias = reinterpret_cast<__half*>(slabs + SLABS * kP2SlabBytes);
+  float2* smr = reinterpret_cast<float2*>(slabs + SLABS * kP2SlabBytes + kP2BiasBytes);  // [2][128] (rstd, -mean * rstd)
+  __half* tvec = reinterpret_cast<__half*>(slabs + SLABS * kP2SlabBytes + kP2BiasBytes + kP2RowStatBytes);  // [2][3][160]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(slabs + SLABS * kP2SlabBytes + kP2BiasBytes + kP2RowStatBytes +
                                                    kP2TileVecBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;  // [2]
@@ -1346,18 +1354,19 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // ===== store warp: slab -> global (TMA store), then recycle the slab: fetch the residual tile of the tile after
     // next into it (residual GEMMs) or declare it free =====
     const bool lead = role_elect();
+    // s_: tile parity (which res_full barrier); the slab is s_ with two slabs, the only one otherwise
     auto request_res = [&](int u_, int s_) {
       int ntile_, mg_, w0_, h0_, n0_;
       decode(u_, ntile_, mg_);
       origin(mg_, w0_, h0_, n0_);
       mbar_expect_tx(&res_full[s_], kP2SlabBytes);
       for (int chunk = 0; chunk < kP2Chunks; ++chunk)
-        tma_load_4d(slabs + s_ * kP2SlabBytes + chunk * kP2ChunkBytes, &tmR, &res_full[s_],
+        tma_load_4d(slabs + (SLABS == 2 ? s_ : 0) * kP2SlabBytes + chunk * kP2ChunkBytes, &tmR, &res_full[s_],
                     ntile_ * kP2BN + chunk * 32, w0_, h0_, n0_);
     };
     if (lead && has_res) {
       if (u_begin < u_end) request_res(u_begin, 0);
-      if (u_begin + u_step < u_end) request_res(u_begin + u_step, 1);
+      if (SLABS == 2 && u_begin + u_step < u_end) request_res(u_begin + u_step, 1);
     }
     int local = 0;
     for (int u = u_begin; u < u_end; u += u_step, ++local) {
@@ -1370,17 +1379,20 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         stamp(local, 9);
         if (p.dbg_skip != 3) {
           for (int chunk = 0; chunk < kP2Chunks; ++chunk)
-            tma_store_4d(&tmD, slabs + s * kP2SlabBytes + chunk * kP2ChunkBytes, ntile * kP2BN + chunk * 32, w0, h0, n0);
+            tma_store_4d(&tmD, slabs + (SLABS == 2 ? s : 0) * kP2SlabBytes + chunk * kP2ChunkBytes,
+                         ntile * kP2BN + chunk * 32, w0, h0, n0);
           bulk_commit_group();
           stamp(local, 10);
           bulk_wait_group_read<0>();  // only this thread waits for the drain
         }
         stamp(local, 11);
-        const int nxt = u + 2 * u_step;
+        // the drained slab goes to the tile after next (two slabs) or to the next tile (one slab: the other parity)
+        const int nxt = u + SLABS * u_step;
+        const int s_nxt = SLABS == 2 ? s : s ^ 1;
         if (has_res) {
-          if (nxt < u_end) request_res(nxt, s);
+          if (nxt < u_end) request_res(nxt, s_nxt);
         } else {
-          mbar_arrive(&slab_free[s]);
+          mbar_arrive(&slab_free[s_nxt]);
         }
         stamp(local, 12);
       }
@@ -1493,7 +1505,7 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     for (int u = u_begin; u < u_end; u += u_step, ++local) {
       const int buf = local & 1;
       const uint32_t ph = (local >> 1) & 1;
-      uint8_t* slab = slabs + buf * kP2SlabBytes;
+      uint8_t* slab = slabs + (SLABS == 2 ? buf : 0) * kP2SlabBytes;
       uint4 bv[5];
       if (has_bias && !staged) {
         const uint4* bsrc = reinterpret_cast<const uint4*>(sbias + ntile * kP2BN + part * 40);
@@ -1536,7 +1548,8 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       tc_fence_before();
       if (lane == 0) mbar_arrive_cluster(buf ? empty_addr1 : empty_addr0);  // accumulator handed back right away
       if (has_res) mbar_wait(&res_full[buf], ph);   // residual landed (the fetch was issued after the slab's last store drained)
-      else mbar_wait(&slab_free[buf], ph ^ 1);      // the slab's previous store has been read out
+      else mbar_wait(&slab_free[buf], SLABS == 1 && buf ? ph : ph ^ 1);  // the slab's previous store has been read out
+      // (one slab: slab_free[1] first fires after tile 0's store, slab_free[0] after tile 1's -- tile 0 itself waits for nothing)
       if (etr) stamp(local, 7);
       // folded LayerNorm (this GEMM's A rows are the un-normalised x): per-row (rstd, -mean * rstd) from the store warp
       float rstd = 1.f, nmr = 0.f;
@@ -1703,12 +1716,12 @@ static int launch_persistent_cs(const CUtensorMap& tmA, const CUtensorMap& tmB, 
   return 0;
 }
 
-template <int STAGES, bool WS, bool AS = false>
+template <int STAGES, bool WS, bool AS = false, int SLABS = 2>
 static int launch_pair160(const CUtensorMap& tmA, const CUtensorMap& tmB2, const CUtensorMap& tmD, const CUtensorMap& tmR,
                           const GemmKParams& kp, int m_tiles, int n_tiles, cudaStream_t stream) {
-  constexpr int smem = pair160_smem_bytes<STAGES, WS>();
+  constexpr int smem = pair160_smem_bytes<STAGES, WS, SLABS>();
   static_assert(smem <= 227 * 1024, "pair160 configuration exceeds shared memory");
-  auto kern = gemm_tc_pair160_kernel<STAGES, WS, 2, AS>;
+  auto kern = gemm_tc_pair160_kernel<STAGES, WS, 2, AS, SLABS>;
   static DeviceOnce configured;
   if (configured.first()) IVV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int groups = (m_tiles + 1) / 2;
@@ -1840,7 +1853,7 @@ namespace ivv {
 // -1 = unset. IVV_HALO / IVV_DS / IVV_EPI2 / IVV_PAIR: 0 disables; IVV_CLUSTER=2, IVV_FORCE_BN=32|64|128|160|256,
 // IVV_NO_WS=1, IVV_DEBUG_SKIP=1..5 (knock-outs, results are garbage).
 struct GemmEnv {
-  int halo, ds, epi2, pair, cluster, force_bn, no_ws, ws, dbg_skip, geglu_ds, cl4, cl4_min, wide, wide_k, as, as_pf;
+  int halo, ds, epi2, pair, cluster, force_bn, no_ws, ws, dbg_skip, geglu_ds, cl4, cl4_min, wide, wide_k, as, as_pf, slab1;
 };
 static const GemmEnv& gemm_env() {
   static const GemmEnv e = [] {
@@ -1865,6 +1878,7 @@ static const GemmEnv& gemm_env() {
     g.wide_k = geti("IVV_WIDE_K");
     g.as = geti("IVV_AS");
     g.as_pf = geti("IVV_AS_PF");
+    g.slab1 = geti("IVV_SLAB1");
     return g;
   }();
   return e;
@@ -2164,6 +2178,9 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
         g_last_as = 1;
         return launch_pair160<5, false, true>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
       }
+      // K >= 640: one output slab and a sixth pipeline stage (see the kernel). IVV_SLAB1=0 disables.
+      if (kp.taps * kp.kblocks >= 10 && env.slab1 != 0)
+        return launch_pair160<6, false, false, 1>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
       return launch_pair160<5, false>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
     }
     if (ds) {
