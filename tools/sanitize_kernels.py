@@ -43,6 +43,9 @@ run("pair160 no-residual 3000x640x1920", lambda: lin(3000, 640, 1920, res=False,
 run("pair160 ghost tile 1152x1280x1280", lambda: lin(1152, 1280, 1280))
 run("v2 pair 256-wide 2000x2560x512", lambda: lin(2000, 2560, 512))
 run("v2 DS 128-wide 3000x256x128", lambda: lin(3000, 256, 128))
+run("pair160 activation-stationary 19000x320x960 (>= 74 M pairs)", lambda: lin(19000, 320, 960, res=False, bias=False))
+run("pair160 one slab / six stages + residual 3000x1280x640", lambda: lin(3000, 1280, 640))
+run("320-wide pair tiles 2880x2560x1280 + residual (register residual, two slabs per group)", lambda: lin(2880, 2560, 1280))
 run("single tile 3x320x1280", lambda: lin(3, 320, 1280, res=False))
 run("ragged N 130x72x40", lambda: lin(130, 72, 40))
 
@@ -55,6 +58,7 @@ def geglu(rows, c):
 run("GEGLU 2000x320", lambda: geglu(2000, 320))
 run("GEGLU 300x1280", lambda: geglu(300, 1280))
 run("GEGLU 6000x320 (several tiles per cluster: staged bias, two output slabs)", lambda: geglu(6000, 320))
+run("GEGLU activation-stationary 19000x320", lambda: geglu(19000, 320))
 
 
 def conv(n, ci, co, h, w, res=False, rowbias=False, f32out=False):
@@ -69,6 +73,7 @@ run("halo conv 16x8 box, 160-wide 6x320x320 32x48 +temb +res", lambda: conv(6, 3
 run("halo conv 8x16 box 4x640x640 16x24", lambda: conv(4, 640, 640, 16, 24))
 run("halo conv 128-wide VAE 2x128x128 64x96", lambda: conv(2, 128, 128, 64, 96))
 run("per-tap conv 8x12 level 16x1280x1280", lambda: conv(16, 1280, 1280, 8, 12))
+run("per-tap conv 8x12 level, 320-wide tiles 30x320x1280 +temb +res", lambda: conv(30, 320, 1280, 8, 12, res=True, rowbias=True))
 run("split-K conv 4x6 level 48x1280x1280", lambda: conv(48, 1280, 1280, 4, 6, res=True))
 run("fp32 head conv 320->4", lambda: conv(2, 320, 4, 32, 48, f32out=True))
 run("stride-2 conv", lambda: ops.conv3x3_s2(h16(4 * 16 * 24, 320), ops.pack_conv3x3_im2col(h16(320, 320, 3, 3, scale=0.02)),
