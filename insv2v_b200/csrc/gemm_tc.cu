@@ -1042,9 +1042,9 @@ constexpr int kP2StageBytes = kABytes + kP2BTileBytes;      // 16 KB activations
 constexpr int kP2WsKBlocks = 5;                             // weight-stationary mode: K <= 320
 constexpr int kP2RowStatBytes = 2 * kBlockM * 8;            // folded LayerNorm: (rstd, -mean * rstd) per row, 2 buffers
 constexpr int kP2TileVecBytes = 2 * 3 * kP2BN * 2;          // folded LayerNorm: bias | row bias | wsum slices of the tile
-template <int STAGES, bool WS, int SLABS = 2>
+template <int STAGES, bool WS, int SLABS = 2, int KB = 1>
 constexpr int pair160_smem_bytes() {
-  return (WS ? STAGES * kABytes + kP2WsKBlocks * kP2BTileBytes : STAGES * kP2StageBytes) + SLABS * kP2SlabBytes +
+  return (WS ? STAGES * kABytes + kP2WsKBlocks * kP2BTileBytes : STAGES * KB * kP2StageBytes) + SLABS * kP2SlabBytes +
          kP2BiasBytes + kP2RowStatBytes + kP2TileVecBytes + 384;
 }
 
@@ -1083,7 +1083,11 @@ constexpr int pair160_smem_bytes() {
 // enough and the 40 KB it frees hold a sixth pipeline stage (+20 % bytes in flight). The slab-state barriers keep
 // alternating with the tile parity (slab_full / slab_free / res_full [local & 1]); only the memory is shared, so the slab
 // of tile i + 1 (residual fetch or "free") is released when the store of tile i has drained, not of tile i - 1.
-template <int STAGES, bool WS, int CL = 2, bool AS = false, int SLABS = 2>
+//
+// KB = 2 (K a multiple of 128): a ring slot holds TWO 64-channel K blocks (two swizzle atoms per operand row, loaded by
+// two TMA boxes each) behind ONE full / empty barrier pair: half as many barrier round trips, waits, commits and
+// producer wake-ups per tile for the same bytes in flight (3 slots x 52 KB = 6 x 26 KB).
+template <int STAGES, bool WS, int CL = 2, bool AS = false, int SLABS = 2, int KB = 1>
 __global__ void __launch_bounds__(kP2Threads, 1)
 gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmR,
@@ -1094,9 +1098,10 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   static_assert(!AS || (!WS && CL == 2), "activation-stationary mode: plain pair clusters");
   static_assert(SLABS == 2 || (SLABS == 1 && !WS && !AS && CL == 2), "single output slab: plain pair clusters");
   static_assert(STAGES <= 6, "barrier block holds six stages");
+  static_assert(KB == 1 || (KB == 2 && !WS && !AS && CL == 2), "two K blocks per ring slot: plain pair clusters");
   constexpr bool C4 = CL == 4;
   constexpr uint32_t kAccStride = 256;  // TMEM columns per accumulator buffer
-  constexpr int kOperandBytes = WS ? STAGES * kABytes + kP2WsKBlocks * kP2BTileBytes : STAGES * kP2StageBytes;
+  constexpr int kOperandBytes = WS ? STAGES * kABytes + kP2WsKBlocks * kP2BTileBytes : STAGES * KB * kP2StageBytes;
   uint8_t* b_res = smem + STAGES * kABytes;  // WS only: [k block][80 weight rows x 128 B]
   uint8_t* slabs = smem + kOperandBytes;
   __half* sbias = reinterpret_cast<__half*>(slabs + SLABS * kP2SlabBytes);
@@ -1234,8 +1239,8 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             cur_nt = ntile;
           }
         }
-        for (int it = 0; it < its_per_tile; ++it) {
-          if (it == 0 || it == its_per_tile - 1) stamp(plocal, it == 0 ? 0 : 1);
+        for (int it = 0; it < its_per_tile; it += KB) {
+          if (it == 0 || it >= its_per_tile - KB) stamp(plocal, it == 0 ? 0 : 1);
           const int tap = it / p.kblocks;
           const int kb = it - tap * p.kblocks;
           int dy = 0, dx = 0;
@@ -1261,6 +1266,16 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           } else if constexpr (WS) {
             if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * kABytes);
             tma_load_4d_2sm(smem + stage * kABytes, &tmA, lead_bar, kb * kBlockK, w0 + dx, h0 + dy, n0);
+          } else if constexpr (KB == 2) {
+            // (linear layers, K % 128 == 0: the host guarantees taps == 1 and an even number of K blocks)
+            uint8_t* sa = smem + stage * (2 * kP2StageBytes);
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], 4 * kP2StageBytes);
+#pragma unroll
+            for (int sub = 0; sub < 2; ++sub) {
+              tma_load_4d_2sm(sa + sub * kP2StageBytes, &tmA, lead_bar, (kb + sub) * kBlockK, w0, h0, n0);
+              tma_load_3d_2sm(sa + sub * kP2StageBytes + kABytes, &tmB, lead_bar, (kb + sub) * kBlockK,
+                              ntile * kP2BN + crank * (kP2BN / 2), 0);
+            }
           } else {
             uint8_t* sa = smem + stage * kP2StageBytes;
             if (crank == 0) mbar_expect_tx(&full_bar[stage], 2 * kP2StageBytes);
@@ -1316,21 +1331,24 @@ gemm_tc_pair160_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         tc_fence_after();
         stamp(local, 2);
         const uint32_t tacc = tmem_base + buf * kAccStride;
-        for (int it = 0; it < its_per_tile; ++it) {
+        for (int it = 0; it < its_per_tile; it += KB) {
           if constexpr (AS) {
             if (as_nt == 0) mbar_wait(&a_full[it], (uint32_t)(as_j & 1));  // resident activation slice of this M pair
           }
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (it == 0) stamp(local, 13);                      // first / last operand stage of the tile seen
-          if (it == its_per_tile - 1) stamp(local, 14);
-          const uint32_t sa = smem_u32(smem + stage * (WS ? kABytes : kP2StageBytes));
-          const uint64_t adesc = umma_desc_kmajor_sw128(AS ? smem_u32(smem + it * kP2StageBytes) : sa);
-          const uint64_t bdesc = umma_desc_kmajor_sw128(WS ? smem_u32(b_res + it * kP2BTileBytes) : sa + kABytes);
+          if (it >= its_per_tile - KB) stamp(local, 14);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            if (p.dbg_skip == 1 && (it | k) != 0) continue;  // tuning only: one MMA per tile
-            umma_f16_ss_2sm(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | k) != 0 ? 1u : 0u);
+          for (int sub = 0; sub < KB; ++sub) {
+            const uint32_t sa = smem_u32(smem + (stage * KB + sub) * (WS ? kABytes : kP2StageBytes));
+            const uint64_t adesc = umma_desc_kmajor_sw128(AS ? smem_u32(smem + it * kP2StageBytes) : sa);
+            const uint64_t bdesc = umma_desc_kmajor_sw128(WS ? smem_u32(b_res + it * kP2BTileBytes) : sa + kABytes);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              if (p.dbg_skip == 1 && (it | sub | k) != 0) continue;  // tuning only: one MMA per tile
+              umma_f16_ss_2sm(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (it | sub | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit_2sm(&empty_bar[stage], kAllMask);
           if constexpr (AS) {
@@ -1716,12 +1734,12 @@ static int launch_persistent_cs(const CUtensorMap& tmA, const CUtensorMap& tmB, 
   return 0;
 }
 
-template <int STAGES, bool WS, bool AS = false, int SLABS = 2>
+template <int STAGES, bool WS, bool AS = false, int SLABS = 2, int KB = 1>
 static int launch_pair160(const CUtensorMap& tmA, const CUtensorMap& tmB2, const CUtensorMap& tmD, const CUtensorMap& tmR,
                           const GemmKParams& kp, int m_tiles, int n_tiles, cudaStream_t stream) {
-  constexpr int smem = pair160_smem_bytes<STAGES, WS, SLABS>();
+  constexpr int smem = pair160_smem_bytes<STAGES, WS, SLABS, KB>();
   static_assert(smem <= 227 * 1024, "pair160 configuration exceeds shared memory");
-  auto kern = gemm_tc_pair160_kernel<STAGES, WS, 2, AS, SLABS>;
+  auto kern = gemm_tc_pair160_kernel<STAGES, WS, 2, AS, SLABS, KB>;
   static DeviceOnce configured;
   if (configured.first()) IVV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int groups = (m_tiles + 1) / 2;
@@ -1853,7 +1871,7 @@ namespace ivv {
 // -1 = unset. IVV_HALO / IVV_DS / IVV_EPI2 / IVV_PAIR: 0 disables; IVV_CLUSTER=2, IVV_FORCE_BN=32|64|128|160|256,
 // IVV_NO_WS=1, IVV_DEBUG_SKIP=1..5 (knock-outs, results are garbage).
 struct GemmEnv {
-  int halo, ds, epi2, pair, cluster, force_bn, no_ws, ws, dbg_skip, geglu_ds, cl4, cl4_min, wide, wide_k, as, as_pf, slab1;
+  int halo, ds, epi2, pair, cluster, force_bn, no_ws, ws, dbg_skip, geglu_ds, cl4, cl4_min, wide, wide_k, as, as_pf, slab1, kb2;
 };
 static const GemmEnv& gemm_env() {
   static const GemmEnv e = [] {
@@ -1879,6 +1897,7 @@ static const GemmEnv& gemm_env() {
     g.as = geti("IVV_AS");
     g.as_pf = geti("IVV_AS_PF");
     g.slab1 = geti("IVV_SLAB1");
+    g.kb2 = geti("IVV_KB2");
     return g;
   }();
   return e;
@@ -2179,6 +2198,10 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
         return launch_pair160<5, false, true>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
       }
       // K >= 640: one output slab and a sixth pipeline stage (see the kernel). IVV_SLAB1=0 disables.
+      // ... and, when K is a multiple of 128, two K blocks per ring slot: half the barrier round trips per tile
+      // (18432x640->1920 49.5 -> 46.4 us, 4608x1280->3840 43.5 -> 39.7, profiles/r02_gemm_kb2_ab.txt). IVV_KB2=0 disables.
+      if (kp.taps == 1 && kp.kblocks >= 10 && (kp.kblocks % 2) == 0 && (a->c % 128) == 0 && env.slab1 != 0 && env.kb2 != 0)
+        return launch_pair160<3, false, false, 1, 2>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
       if (kp.taps * kp.kblocks >= 10 && env.slab1 != 0)
         return launch_pair160<6, false, false, 1>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);
       return launch_pair160<5, false>(tmA, tmB2, tmD, tmR, kp, m_tiles, n_tiles, stream);

@@ -1,5 +1,5 @@
 """One eager UNet3D forward at a given latent shape under the default kernel selection and with the third-session GEMM
-variants switched off (IVV_WIDE=0 IVV_AS=0 IVV_SLAB1=0), one subprocess each, same seeded weights and inputs: the outputs
+variants switched off (IVV_WIDE=0 IVV_AS=0 IVV_SLAB1=0 IVV_KB2=0), one subprocess each, same seeded weights and inputs: the outputs
 must agree to fp16 rounding (same K order, different tiles). Covers shapes that have no CPU golden (48x72 latents).
 Usage: python tools/variant_consistency.py [F,H,W ...]      (default 16,48,72 and 16,32,48)"""
 import os
@@ -33,7 +33,7 @@ if __name__ == "__main__":
         child(tuple(int(v) for v in sys.argv[2].split(",")), sys.argv[3])
         sys.exit(0)
     shapes = sys.argv[1:] or ["16,48,72", "16,32,48"]
-    off = dict(IVV_WIDE="0", IVV_AS="0", IVV_SLAB1="0")
+    off = dict(IVV_WIDE="0", IVV_AS="0", IVV_SLAB1="0", IVV_KB2="0")
     worst = 0.0
     for sh in shapes:
         outs = []
