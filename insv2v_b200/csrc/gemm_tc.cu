@@ -1930,6 +1930,10 @@ extern "C" int ivv_debug_cl4_clusters() { return ivv::pair160_cl4_clusters<5>();
 
 // tuning / test hook (not in ivv.h): tile width (BLOCK_N) the calling thread's last ivv_gemm chose
 static thread_local int g_last_bn = 0, g_last_as = 0;
+// test hook (not in ivv.h): while set, the calling thread's ivv_gemm validates its arguments, chooses the pixel box and the
+// tile width (ivv_debug_last_gemm_tile) and returns before it touches the device -- the host logic, testable without a GPU
+static thread_local bool g_plan_only = false;
+extern "C" void ivv_debug_gemm_plan_only(int on) { g_plan_only = on != 0; }
 extern "C" int ivv_debug_last_gemm_tile() { return g_last_bn; }
 // 1 if the calling thread's last ivv_gemm ran the activation-stationary mode of the short-K pair kernel
 extern "C" int ivv_debug_last_gemm_as() { return g_last_as; }
@@ -2107,6 +2111,7 @@ extern "C" int ivv_gemm(const ivv_gemm_args* a, ivv_stream_t stream_) {
   const int n_tiles = (int)((a->n_out + bn_sel - 1) / bn_sel);
   g_last_bn = bn_sel;
   g_last_as = 0;
+  if (g_plan_only) return 0;
 
   // ---- tensor maps ----
   CUtensorMap tmA, tmB, tmB2;

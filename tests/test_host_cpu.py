@@ -224,6 +224,57 @@ def test_conv_box_choice_and_halo_eligibility():
         assert tiles(d, e, g) == tiles(a, b, c)
 
 
+def test_gemm_tile_width_choice_for_the_unet_shapes():
+    """Host logic of ivv_gemm, second part: the tile width it picks for the GEMM shapes of the configs[1] forward (148 SMs
+    assumed when there is no device). Plan-only calls: arguments are validated, box and tile width chosen, nothing launched."""
+    import ctypes
+    from insv2v_b200 import lib
+    L = lib.load()
+    L.ivv_debug_gemm_plan_only.argtypes = [ctypes.c_int]
+    L.ivv_debug_gemm_plan_only.restype = None
+
+    def tile(n_img, h, w, c, n_out, taps=1, residual=False, geglu=False, row_stats=False, expect_ok=True):
+        a = lib.GemmArgs()
+        fake = 1 << 20  # 16-byte aligned, never dereferenced in plan-only mode
+        a.a, a.n_img, a.h, a.w, a.c, a.a_ld = fake, n_img, h, w, c, c
+        a.wgt, a.n_out, a.w_ld, a.taps, a.geglu = fake, n_out, c, taps, int(geglu)
+        a.d, a.d_ld = fake, (n_out // 2 if geglu else n_out)
+        if residual:
+            a.residual, a.res_ld = fake, n_out
+        if row_stats:
+            a.row_stats_out = fake
+        L.ivv_debug_gemm_plan_only(1)
+        try:
+            rc = L.ivv_gemm(ctypes.byref(a), None)
+        finally:
+            L.ivv_debug_gemm_plan_only(0)
+        assert (rc == 0) == expect_ok, L.ivv_last_error()
+        return L.ivv_debug_last_gemm_tile() if rc == 0 else None
+
+    rows = lambda r: dict(n_img=1, h=1, w=r)
+    # 320-wide pair tiles: the N = 1280 layers of the 8x12 level (36 M tiles -> 72 tiles = one round of the 74 clusters)
+    for c in (640, 1280, 1920, 2560):
+        assert tile(48, 8, 12, c, 1280, taps=9) == 320
+    assert tile(48, 8, 12, 1280, 1280, taps=9, residual=True) == 320
+    assert tile(**rows(4608), c=5120, n_out=1280, residual=True) == 320   # FF out-projection of that level
+    assert tile(**rows(4608), c=2560, n_out=1280) == 320                  # its 1x1 shortcuts
+    # ... but not where the short-K pair kernel (160-wide tiles) serves: K <= 1280, and never for a LayerNorm-fold producer
+    assert tile(**rows(4608), c=1280, n_out=1280, residual=True) == 160
+    assert tile(**rows(73728), c=1280, n_out=320, residual=True) == 160
+    assert tile(**rows(4608), c=1280, n_out=1280, residual=True, row_stats=True) == 160
+    for r, c, n in [(73728, 320, 960), (18432, 640, 1920), (4608, 1280, 3840), (73728, 320, 320), (18432, 640, 640)]:
+        assert tile(**rows(r), c=c, n_out=n) == 160
+    # the 4x6 level has too few M tiles for the wide tile to save a round; the 32x48 / 16x24 halo convolutions keep 160 / 256
+    assert tile(48, 4, 6, 1280, 1280, taps=9) != 320
+    assert tile(48, 32, 48, 320, 320, taps=9) == 160
+    assert tile(48, 16, 24, 640, 640, taps=9) in (160, 256)
+    # GEGLU GEMMs: always 256 (128 hidden | 128 gate columns per tile)
+    assert tile(**rows(73728), c=320, n_out=2560, geglu=True) == 256
+    # argument errors are reported before anything is planned
+    assert tile(**rows(4608), c=1284, n_out=1280, expect_ok=False) is None          # a_ld not a multiple of 8
+    assert tile(**rows(4608), c=1280, n_out=1000, geglu=True, expect_ok=False) is None  # GEGLU needs n_out % 256 == 0
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # packed-weight invalidation (a forward before the checkpoint load must not leave stale fp16 weights / graphs behind)
 # ------------------------------------------------------------------------------------------------------------------
